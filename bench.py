@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""Headline benchmark: dMel encode audio-seconds per second (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of BASELINE configs[1]:
+64 utterances x 10 s, 24 kHz, n_fft 1024, hop 256, 128 mel, 16 bins —
+fused encode (waveform -> uint8 codes) followed by dequantise (codes -> mel).
+With N GPUs every rank runs that batch on its own shard of utterances (weak
+scaling, no data-path collective; the calibration all-reduce happens once,
+before the timed region).  Prints ONE JSON line on rank 0.
+
+``--impl reference`` times the CPU oracle port of the reference's torch path
+(oracle/dmel_oracle.py; the reference is Python, so there is no oracle/_ref)
+on the host cores for the same batch.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# ---- workload: BASELINE.json configs[1] -------------------------------------
+SAMPLE_RATE = 24000
+SECONDS = 10
+BATCH = 64
+N_BINS = 16
+GEOM = dict(sample_rate=SAMPLE_RATE, n_fft=1024, win_length=1024, hop_length=256, n_mels=128, f_min=0.0, f_max=12000.0)
+N_SAMPLES = SAMPLE_RATE * SECONDS
+N_FRAMES = N_SAMPLES // GEOM["hop_length"]
+AUDIO_SEC_PER_BATCH = BATCH * SECONDS
+ENCODE_BYTES = 4 * BATCH * N_SAMPLES + BATCH * GEOM["n_mels"] * N_FRAMES
+DEQUANT_BYTES = 5 * BATCH * GEOM["n_mels"] * N_FRAMES
+RING = 4  # distinct input batches cycled through so no step finds its input in the 126 MB L2
+METRIC = "dmel_encode_audio_seconds_per_second"
+UNIT = "audio-s/s"
+WORKLOAD = ("configs[1]: 24 kHz speech, 128 mel, 16 bins, batch 64x10 s, n_fft 1024, hop 256; "
+            "step = fused encode (wav->u8 codes) + dequant (codes->mel)")
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_step(wav, cfg, bank, lo, hi):
+    from oracle import dmel_oracle as O
+    codes = O.dmel_encode(O.log_mel(wav, cfg, bank), lo, hi, N_BINS)
+    return O.dmel_decode(codes, lo, hi, N_BINS)
+
+
+def cpu_oracle_setup(rows: int):
+    from dmel_codec_b200 import synth
+    from oracle import dmel_oracle as O
+    cfg = O.MelConfig(**GEOM)
+    bank = torch.from_numpy(O.slaney_filterbank(SAMPLE_RATE, GEOM["n_fft"], GEOM["n_mels"], GEOM["f_min"], GEOM["f_max"]))
+    wav = synth.batch(range(rows), N_SAMPLES, SAMPLE_RATE, "speech")
+    lo, hi = O.calibrate_minmax(O.log_mel(wav[: min(rows, 4)], cfg, bank))
+    return wav, cfg, bank, lo, hi
+
+
+def run_reference(args, rank: int):
+    """The reference's CPU path (oracle port) on the host cores, same batch."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wav, cfg, bank, lo, hi = cpu_oracle_setup(BATCH)
+    for _ in range(args.warmup):
+        oracle_step(wav, cfg, bank, lo, hi)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_step(wav, cfg, bank, lo, hi)
+    dt = time.perf_counter() - t0
+    value = AUDIO_SEC_PER_BATCH * args.steps / dt
+    sample = f"{BATCH} x {SECONDS} s per step, {args.steps} steps, torch {torch.__version__} CPU ops, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU oracle port of reference utils/spectrogram.py + Appendix-B quantiser"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch.distributed as dist
+    import dmel_codec_b200 as d
+    from dmel_codec_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: dmel_codec_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    tok = d.DMelTokenizer(n_bins=N_BINS, **GEOM).to(dev)
+
+    # this rank's shard: utterance ids [rank*RING*BATCH, ...): RING distinct batches
+    base = rank * RING * BATCH
+    ring = [synth.device_batch(range(base + r * BATCH, base + (r + 1) * BATCH), N_SAMPLES, SAMPLE_RATE, dev)
+            for r in range(RING)]
+    # dataset-wide calibration: local min/max then the one all-reduce of the path
+    tok.calibrate(ring)
+    q = tok.quantizer
+    plan = tok._plan(dev)
+    lo, scale, table = q.lo, q.scale(), q.table()
+    torch.cuda.synchronize()
+
+    from dmel_codec_b200 import plan as P
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i, ev=None):
+        wav = ring[i % RING]
+        if ev:
+            ev[0].record(stream)
+        codes = plan.encode(wav, None, lo, scale, N_BINS)
+        if ev:
+            ev[1].record(stream)
+        mel = P.dequantize(codes, table)
+        if ev:
+            ev[2].record(stream)
+        return codes, mel
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        torch.cuda.synchronize()
+        wall0 = time.perf_counter()
+        for i in range(args.steps):
+            step(args.warmup + i, events[i])
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - wall0
+    if world > 1:
+        dist.barrier()
+    enc_ms = [e[0].elapsed_time(e[1]) for e in events]
+    deq_ms = [e[1].elapsed_time(e[2]) for e in events]
+    total_ms = events[0][0].elapsed_time(events[-1][2])  # device time of the K back-to-back steps
+    t = torch.tensor([total_ms, sum(enc_ms), sum(deq_ms), wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, enc_total, deq_total, wall_ms = t.tolist()
+
+    # ---- end to end through the public API with HOST buffers -------------------
+    host = [ring[r].cpu().pin_memory() for r in range(2)]
+    out = torch.empty((BATCH, GEOM["n_mels"], N_FRAMES), dtype=torch.uint8).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for r in range(2):
+        tok.encode_host(host[r], out=out)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        tok.encode_host(host[i % 2], out=out)  # returns after codes are in host memory
+    e2e_dt = time.perf_counter() - t0
+    e = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    e2e_value = world * AUDIO_SEC_PER_BATCH * e2e_steps / e.item()
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    enc_avg_s = enc_total / args.steps / 1e3
+    achieved = ENCODE_BYTES / enc_avg_s / 1e9
+    deq_gbs = DEQUANT_BYTES / (deq_total / args.steps / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "encode_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+
+    # CPU baseline: the oracle port on this box's host cores, bounded sample
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cwav, cfg, bank, clo, chi = cpu_oracle_setup(BATCH)
+    oracle_step(cwav, cfg, bank, clo, chi)
+    passes, c0 = 0, time.perf_counter()
+    while passes < 3 or (time.perf_counter() - c0 < 10.0 and passes < 200):
+        oracle_step(cwav, cfg, bank, clo, chi)
+        passes += 1
+    cpu_dt = time.perf_counter() - c0
+    cpu_value = AUDIO_SEC_PER_BATCH * passes / cpu_dt
+
+    value = world * AUDIO_SEC_PER_BATCH * args.steps / (total_ms / 1e3)
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": f"{BATCH}x{SECONDS}s", "sharding": "utterances, no data-path collective",
+                   "l2": f"inputs cycle through a ring of {RING} distinct batches ({RING * ENCODE_BYTES / 1e6:.0f} MB > 126 MB L2)",
+                   "wall_ms_per_step": wall_ms / args.steps},
+        "roofline": {"bound": "hbm", "kernel": "dmel_fused_kernel<1024,32> (encode)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ENCODE_BYTES, "avg_launch_ms": enc_avg_s * 1e3,
+                     "dequant": {"achieved": deq_gbs, "frac": deq_gbs / peak, "algorithmic_bytes_per_launch": DEQUANT_BYTES,
+                                 "avg_launch_ms": deq_total / args.steps}},
+        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{passes} passes of the same {BATCH}x{SECONDS}s batch, oracle/dmel_oracle.py, torch CPU, {cores} threads, {cpu_dt:.1f} s"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * BATCH * N_SAMPLES,
+                "d2h_bytes_per_step": BATCH * GEOM["n_mels"] * N_FRAMES, "steps": e2e_steps,
+                "call": "DMelTokenizer.encode_host -> dmel_encode_host_u8 (pinned host wav in, host codes out)"},
+        "gpu_launches": 2 * args.steps,
+        "clocks": clocks.summary(),
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

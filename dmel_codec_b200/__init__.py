@@ -1,0 +1,17 @@
+"""dmel_codec_b200 — B200-native dMel tokenization hot path.
+
+Public surface (drop-in for the reference's ``dmel_codec.utils.spectrogram``
+plus the dMel quantiser the reference's README describes but does not ship):
+
+    LinearSpectrogram, LogMelSpectrogram      waveform -> log-mel
+    DMelQuantizer, DMelResult                 log-mel <-> uint8 codes, calibration
+    DMelTokenizer                             waveform -> codes (fused kernel)
+
+Everything computes in hand-written sm_100a CUDA reached through the C ABI in
+``include/dmel_b200.h``; importing the package is cheap, the first call loads
+``libdmel_b200.so`` and raises if it was not built.
+"""
+from .spectrogram import LinearSpectrogram, LogMelSpectrogram
+from .quantizer import DMelQuantizer, DMelResult, DMelTokenizer
+
+__all__ = ["LinearSpectrogram", "LogMelSpectrogram", "DMelQuantizer", "DMelResult", "DMelTokenizer"]

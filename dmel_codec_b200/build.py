@@ -1,0 +1,55 @@
+"""Build ``libdmel_b200.so`` in-tree with nvcc for sm_100a.
+
+    python -m dmel_codec_b200.build [--force]
+
+nvcc cross-compiles without a GPU; the resulting .so is git-ignored but travels
+to the GPU box with the repo snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libdmel_b200.so")
+SOURCES = ["dmel_b200.cu"]
+DEPS = ["dmel_b200.cu", "logmel_kernel.cuh", "fft_core.cuh", "codec_kernels.cuh",
+        os.path.join("..", "..", "include", "dmel_b200.h")]
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
+
+
+def find_nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: set NVCC or put /usr/local/cuda/bin on PATH")
+
+
+def is_stale() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    built = os.path.getmtime(OUT)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > built for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return OUT
+    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", OUT, *[os.path.join(CSRC, s) for s in SOURCES]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

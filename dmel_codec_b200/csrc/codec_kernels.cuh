@@ -1,0 +1,147 @@
+// Streaming kernels of the dMel quantiser that work on an existing
+// (B, n_mels, T) tensor: quantise, dequantise, min/max.  All HBM-bound; each
+// warp instruction touches contiguous bytes (128 B of codes / 512 B of floats).
+// The quantiser itself is not in the reference; the spec is SURVEY.md Appendix B.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dmel {
+
+constexpr int kStreamThreads = 256;
+constexpr int kStreamUnroll = 4;  // groups of 4 elements per thread per trip
+
+// ---------------------------------------------------------------------------
+// codes (uint8) -> bin centres (float32) by table lookup.  The table is built
+// by the host with the oracle's exact op order, so the result is bit exact by
+// construction.  Flat indexing: element e belongs to channel (e / T) % M.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStreamThreads) dequantize_kernel(
+    const uint8_t* __restrict__ codes, float* __restrict__ out, const float* __restrict__ table,
+    unsigned n_elems, unsigned n_frames, unsigned n_mels, unsigned n_bins, bool vec_ok) {
+  const unsigned groups = n_elems >> 2;
+  const unsigned stride = gridDim.x * kStreamThreads;
+  const unsigned kmax = n_bins - 1;
+  if (vec_ok) {
+    for (unsigned g0 = blockIdx.x * kStreamThreads + threadIdx.x; g0 < groups; g0 += stride * kStreamUnroll) {
+      uchar4 c[kStreamUnroll];
+#pragma unroll
+      for (int u = 0; u < kStreamUnroll; ++u) {
+        const unsigned g = g0 + u * stride;
+        c[u] = g < groups ? __ldcs(reinterpret_cast<const uchar4*>(codes) + g) : make_uchar4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < kStreamUnroll; ++u) {
+        const unsigned g = g0 + u * stride;
+        if (g >= groups) continue;
+        const unsigned e = g << 2;
+        unsigned rowi = e / n_frames;
+        unsigned t = e - rowi * n_frames;
+        unsigned m = rowi % n_mels;
+        const unsigned char cc[4] = {c[u].x, c[u].y, c[u].z, c[u].w};
+        float r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          r[i] = __ldg(table + m * n_bins + min((unsigned)cc[i], kmax));
+          if (++t == n_frames) { t = 0; m = (m + 1 == n_mels) ? 0 : m + 1; }
+        }
+        __stcs(reinterpret_cast<float4*>(out) + g, make_float4(r[0], r[1], r[2], r[3]));
+      }
+    }
+  }
+  // tail (and the whole tensor when the pointers are not 16-byte aligned)
+  const unsigned first = vec_ok ? (groups << 2) : 0;
+  for (unsigned e = first + blockIdx.x * kStreamThreads + threadIdx.x; e < n_elems; e += stride) {
+    const unsigned m = (e / n_frames) % n_mels;
+    out[e] = __ldg(table + m * n_bins + min((unsigned)codes[e], kmax));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// log-mel (float32) -> codes (uint8):  clamp(floor((x - lo) * scale), 0, K-1)
+// subtraction and multiply kept un-contracted so codes are bit exact for
+// bit-identical x.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned char quantize_one(float x, float lo, float scale, float kmax) {
+  const float pos = __fmul_rn(__fsub_rn(x, lo), scale);
+  return (unsigned char)fminf(fmaxf(floorf(pos), 0.f), kmax);
+}
+
+__global__ void __launch_bounds__(kStreamThreads) quantize_kernel(
+    const float* __restrict__ mel, uint8_t* __restrict__ codes, const float* __restrict__ lo,
+    const float* __restrict__ scale, unsigned n_elems, unsigned n_frames, unsigned n_mels,
+    unsigned n_bins, bool vec_ok) {
+  const unsigned groups = n_elems >> 2;
+  const unsigned stride = gridDim.x * kStreamThreads;
+  const float kmax = float(n_bins - 1);
+  if (vec_ok) {
+    for (unsigned g0 = blockIdx.x * kStreamThreads + threadIdx.x; g0 < groups; g0 += stride * kStreamUnroll) {
+      float4 x[kStreamUnroll];
+#pragma unroll
+      for (int u = 0; u < kStreamUnroll; ++u) {
+        const unsigned g = g0 + u * stride;
+        x[u] = g < groups ? __ldcs(reinterpret_cast<const float4*>(mel) + g) : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < kStreamUnroll; ++u) {
+        const unsigned g = g0 + u * stride;
+        if (g >= groups) continue;
+        const unsigned e = g << 2;
+        unsigned rowi = e / n_frames;
+        unsigned t = e - rowi * n_frames;
+        unsigned m = rowi % n_mels;
+        const float xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+        unsigned char r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          r[i] = quantize_one(xs[i], __ldg(lo + m), __ldg(scale + m), kmax);
+          if (++t == n_frames) { t = 0; m = (m + 1 == n_mels) ? 0 : m + 1; }
+        }
+        reinterpret_cast<uchar4*>(codes)[g] = make_uchar4(r[0], r[1], r[2], r[3]);
+      }
+    }
+  }
+  const unsigned first = vec_ok ? (groups << 2) : 0;
+  for (unsigned e = first + blockIdx.x * kStreamThreads + threadIdx.x; e < n_elems; e += stride) {
+    const unsigned m = (e / n_frames) % n_mels;
+    codes[e] = quantize_one(mel[e], __ldg(lo + m), __ldg(scale + m), kmax);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// per-channel running min / max over valid frames of a (B, M, T) tensor.
+// One warp per (row, channel) line; exact and order independent.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStreamThreads) tensor_minmax_kernel(
+    const float* __restrict__ mel, const int* __restrict__ n_valid, float* run_min, float* run_max,
+    unsigned n_lines, unsigned n_frames, unsigned n_mels) {
+  const unsigned warps_per_block = kStreamThreads / 32;
+  const unsigned lane = threadIdx.x & 31;
+  for (unsigned line = blockIdx.x * warps_per_block + (threadIdx.x >> 5); line < n_lines;
+       line += gridDim.x * warps_per_block) {
+    const unsigned b = line / n_mels, m = line - b * n_mels;
+    unsigned nv = n_frames;
+    if (n_valid) {
+      const int v = n_valid[b];
+      nv = v < 0 ? 0u : (unsigned(v) < n_frames ? unsigned(v) : n_frames);
+    }
+    const float* src = mel + (size_t)line * n_frames;
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float(0xff800000);
+    for (unsigned t = lane; t < nv; t += 32) {
+      const float x = __ldcs(src + t);
+      lo = fminf(lo, x);
+      hi = fmaxf(hi, x);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if (lane == 0 && lo <= hi) {
+      atomic_min_float(run_min + m, lo);
+      atomic_max_float(run_max + m, hi);
+    }
+  }
+}
+
+}  // namespace dmel

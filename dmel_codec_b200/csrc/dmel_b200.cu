@@ -1,0 +1,509 @@
+// C ABI of the B200 dMel tokenization path (see include/dmel_b200.h).
+// Host side: plan construction (banded filterbank, twiddle tables), argument
+// checking, kernel launches.  No torch, no cuFFT, no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/dmel_b200.h"
+#include "logmel_kernel.cuh"
+#include "codec_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define DMEL_CUDA(expr)                                                                  \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return fail(DMEL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+template <typename T>
+cudaError_t upload(T** dev, const std::vector<T>& host) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dev), std::max<size_t>(host.size(), 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  if (host.empty()) return cudaSuccess;
+  return cudaMemcpy(*dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+}  // namespace
+
+struct dmel_plan {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem = 0;
+  int n_fft = 0, hop = 0, n_mels = 0, center = 0;
+  int pad_inner = 0, pad_outer = 0;
+  int tile_frames = 0;  // TF chosen for this geometry
+  int wave_len = 0;
+  int nnz = 0;
+  size_t smem_bytes = 0;
+  float* d_window = nullptr;
+  float2* d_stage_tw = nullptr;
+  float2* d_fold_tw = nullptr;
+  int4* d_chan = nullptr;
+  float* d_weights = nullptr;
+  // scratch for the host-buffer entry point (grown on demand)
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  float* d_wav[2] = {nullptr, nullptr};
+  uint8_t* d_codes[2] = {nullptr, nullptr};
+  int32_t* d_len[2] = {nullptr, nullptr};
+  float* d_lo = nullptr;
+  float* d_scale = nullptr;
+  size_t wav_cap = 0, codes_cap = 0, len_cap = 0;
+};
+
+namespace {
+
+using dmel::FusedParams;
+
+template <int NFFT, int TF>
+size_t fused_smem(int wave_len, int n_mels, int nnz) {
+  return dmel::FusedLayout<NFFT, TF>::total(wave_len, n_mels, nnz);
+}
+
+size_t fused_smem_for(int n_fft, int tf, int wave_len, int n_mels, int nnz) {
+  if (n_fft == 1024) {
+    if (tf == 32) return fused_smem<1024, 32>(wave_len, n_mels, nnz);
+    if (tf == 16) return fused_smem<1024, 16>(wave_len, n_mels, nnz);
+    return fused_smem<1024, 8>(wave_len, n_mels, nnz);
+  }
+  if (tf == 32) return fused_smem<2048, 32>(wave_len, n_mels, nnz);
+  if (tf == 16) return fused_smem<2048, 16>(wave_len, n_mels, nnz);
+  return fused_smem<2048, 8>(wave_len, n_mels, nnz);
+}
+
+template <int NFFT, int TF>
+cudaError_t launch_fused(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st) {
+  auto kern = dmel::dmel_fused_kernel<NFFT, TF>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, dmel::kThreads, plan->smem_bytes, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st) {
+  const int tf = plan->tile_frames;
+  if (plan->n_fft == 1024) {
+    if (tf == 32) return launch_fused<1024, 32>(plan, p, grid, st);
+    if (tf == 16) return launch_fused<1024, 16>(plan, p, grid, st);
+    return launch_fused<1024, 8>(plan, p, grid, st);
+  }
+  if (tf == 32) return launch_fused<2048, 32>(plan, p, grid, st);
+  if (tf == 16) return launch_fused<2048, 16>(plan, p, grid, st);
+  return launch_fused<2048, 8>(plan, p, grid, st);
+}
+
+long long num_frames(const dmel_plan* plan, long long n_samples) {
+  const long long padded = n_samples + 2LL * plan->pad_inner + 2LL * plan->pad_outer;
+  if (padded < plan->n_fft) return 0;
+  return 1 + (padded - plan->n_fft) / plan->hop;
+}
+
+// shared argument checks + parameter block for the three fused entry points
+int prepare_fused(dmel_plan* plan, const float* wav, long long n_rows, long long n_samples,
+                  long long row_stride, FusedParams* p, int* grid) {
+  if (!plan) return fail(DMEL_ERR_INVALID, "plan is null");
+  if (!wav) return fail(DMEL_ERR_INVALID, "waveform pointer is null");
+  if (n_rows < 0 || n_samples <= 0 || row_stride < n_samples)
+    return fail(DMEL_ERR_INVALID, "bad waveform shape: rows=%lld samples=%lld stride=%lld", n_rows, n_samples, row_stride);
+  if (n_samples <= plan->pad_inner)
+    return fail(DMEL_ERR_INVALID,
+                "reflect padding of %d needs more than %d samples per row, got %lld "
+                "(the reference's F.pad raises here too)", plan->pad_inner, plan->pad_inner, n_samples);
+  if (plan->pad_outer && n_samples + 2LL * plan->pad_inner <= plan->pad_outer)
+    return fail(DMEL_ERR_INVALID, "center=True reflect padding of %d needs a longer row", plan->pad_outer);
+  if (n_samples > (1LL << 30)) return fail(DMEL_ERR_INVALID, "rows longer than 2^30 samples are not supported");
+  const long long T = num_frames(plan, n_samples);
+  if (T <= 0) return fail(DMEL_ERR_INVALID, "row of %lld samples is shorter than one frame", n_samples);
+  const long long tiles_per_row = (T + plan->tile_frames - 1) / plan->tile_frames;
+  const long long n_tiles = tiles_per_row * n_rows;
+  if (n_tiles > 0x7fffffffLL) return fail(DMEL_ERR_INVALID, "batch too large: %lld tiles", n_tiles);
+  std::memset(p, 0, sizeof(*p));
+  p->wav = wav;
+  p->row_stride = row_stride;
+  p->n_rows = (int)n_rows;
+  p->n_samples = (int)n_samples;
+  p->n_frames = (int)T;
+  p->tiles_per_row = (int)tiles_per_row;
+  p->n_tiles = (int)n_tiles;
+  p->hop = plan->hop;
+  p->pad_inner = plan->pad_inner;
+  p->pad_outer = plan->pad_outer;
+  p->n_mels = plan->n_mels;
+  p->wave_len = plan->wave_len;
+  p->nnz = plan->nnz;
+  p->window = plan->d_window;
+  p->stage_tw = plan->d_stage_tw;
+  p->fold_tw = plan->d_fold_tw;
+  p->chan = plan->d_chan;
+  p->weights = plan->d_weights;
+  p->n_bins = 1;
+  *grid = (int)std::min<long long>(n_tiles, plan->sm_count);
+  return DMEL_OK;
+}
+
+int check_bins(int n_bins) {
+  if (n_bins < 1 || n_bins > 256) return fail(DMEL_ERR_INVALID, "n_bins must be in [1, 256] for uint8 codes, got %d", n_bins);
+  return DMEL_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int stream_grid(const dmel_plan* /*unused*/, unsigned n_groups) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long want = (n_groups + dmel::kStreamThreads * dmel::kStreamUnroll - 1LL) /
+                         (dmel::kStreamThreads * dmel::kStreamUnroll);
+  return (int)std::max<long long>(1, std::min<long long>(want, 8LL * sms));
+}
+
+}  // namespace
+
+extern "C" {
+
+int dmel_abi_version(void) { return DMEL_ABI_VERSION; }
+
+const char* dmel_last_error(void) { return g_last_error.c_str(); }
+
+int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const float* mel_basis_host,
+                     const float* window_host, dmel_plan** out) {
+  if (!out) return fail(DMEL_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (!mel_basis_host || !window_host) return fail(DMEL_ERR_INVALID, "mel_basis_host / window_host is null");
+  if (n_fft != 1024 && n_fft != 2048)
+    return fail(DMEL_ERR_UNSUPPORTED, "n_fft=%d: this build has kernels for n_fft 1024 and 2048 only", n_fft);
+  if (hop_length < 1 || hop_length > n_fft)
+    return fail(DMEL_ERR_INVALID, "hop_length must be in [1, n_fft], got %d", hop_length);
+  if (n_mels < 1 || n_mels > 1024) return fail(DMEL_ERR_INVALID, "n_mels must be in [1, 1024], got %d", n_mels);
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return fail(DMEL_ERR_NO_DEVICE, "no CUDA device visible; dmel_b200 has no CPU path");
+  }
+  dmel_plan* plan = new (std::nothrow) dmel_plan();
+  if (!plan) return fail(DMEL_ERR_INVALID, "out of host memory");
+  DMEL_CUDA(cudaGetDevice(&plan->device));
+  DMEL_CUDA(cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, plan->device));
+  DMEL_CUDA(cudaDeviceGetAttribute(&plan->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, plan->device));
+  plan->n_fft = n_fft;
+  plan->hop = hop_length;
+  plan->n_mels = n_mels;
+  plan->center = center ? 1 : 0;
+  plan->pad_inner = (n_fft - hop_length) / 2;  // reference utils/spectrogram.py:58
+  plan->pad_outer = center ? n_fft / 2 : 0;
+
+  // banded filterbank: per channel the contiguous non-zero span, padded to x4
+  const int n_freq = n_fft / 2 + 1;
+  std::vector<int4> chan(n_mels);
+  std::vector<float> weights;
+  for (int m = 0; m < n_mels; ++m) {
+    const float* row = mel_basis_host + (size_t)m * n_freq;
+    int first = -1, last = -1;
+    for (int f = 0; f < n_freq; ++f) {
+      if (!std::isfinite(row[f])) {
+        delete plan;
+        return fail(DMEL_ERR_INVALID, "mel_basis[%d][%d] is not finite", m, f);
+      }
+      if (row[f] != 0.f) {
+        if (first < 0) first = f;
+        last = f;
+      }
+    }
+    const int count = first < 0 ? 0 : last - first + 1;
+    const int count4 = (count + 3) / 4 * 4;
+    chan[m] = make_int4(first < 0 ? 0 : first, count4, (int)weights.size(), 0);
+    for (int i = 0; i < count4; ++i) weights.push_back(i < count ? row[first + i] : 0.f);
+  }
+  plan->nnz = (int)weights.size();
+
+  // largest frame tile whose shared-memory footprint fits
+  const int candidates[3] = {32, 16, 8};
+  for (int tf : candidates) {
+    const int wave_len = ((tf - 1) * hop_length + n_fft + 3) / 4 * 4;
+    const size_t need = fused_smem_for(n_fft, tf, wave_len, n_mels, plan->nnz);
+    if (need <= (size_t)plan->max_smem) {
+      plan->tile_frames = tf;
+      plan->wave_len = wave_len;
+      plan->smem_bytes = need;
+      break;
+    }
+  }
+  if (!plan->tile_frames) {
+    const int max_smem = plan->max_smem;
+    delete plan;
+    return fail(DMEL_ERR_UNSUPPORTED, "geometry needs more than %d bytes of shared memory per CTA", max_smem);
+  }
+
+  std::vector<float> window(window_host, window_host + n_fft);
+  std::vector<float2> stage_tw(32 * 32), fold_tw(513);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int k1 = 0; k1 < 32; ++k1)
+    for (int n2 = 0; n2 < 32; ++n2) {
+      const double a = -two_pi * double((k1 * n2) % 1024) / 1024.0;
+      stage_tw[k1 * 32 + n2] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+  for (int k = 0; k <= 512; ++k) {
+    const double a = -two_pi * double(k) / 2048.0;
+    fold_tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+  cudaError_t e = upload(&plan->d_window, window);
+  if (e == cudaSuccess) e = upload(&plan->d_stage_tw, stage_tw);
+  if (e == cudaSuccess) e = upload(&plan->d_fold_tw, fold_tw);
+  if (e == cudaSuccess) e = upload(&plan->d_chan, chan);
+  if (e == cudaSuccess) e = upload(&plan->d_weights, weights);
+  if (e != cudaSuccess) {
+    dmel_plan_destroy(plan);
+    return fail(DMEL_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(e));
+  }
+  *out = plan;
+  return DMEL_OK;
+}
+
+void dmel_plan_destroy(dmel_plan* plan) {
+  if (!plan) return;
+  DeviceGuard guard(plan->device);
+  cudaFree(plan->d_window);
+  cudaFree(plan->d_stage_tw);
+  cudaFree(plan->d_fold_tw);
+  cudaFree(plan->d_chan);
+  cudaFree(plan->d_weights);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(plan->d_wav[i]);
+    cudaFree(plan->d_codes[i]);
+    cudaFree(plan->d_len[i]);
+    if (plan->streams[i]) cudaStreamDestroy(plan->streams[i]);
+  }
+  cudaFree(plan->d_lo);
+  cudaFree(plan->d_scale);
+  delete plan;
+}
+
+long long dmel_plan_num_frames(const dmel_plan* plan, long long n_samples) {
+  if (!plan) return 0;
+  return num_frames(plan, n_samples);
+}
+
+int dmel_logmel_f32(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
+                    long long row_stride, float* logmel_dev, void* stream) {
+  FusedParams p;
+  int grid = 0;
+  int rc = prepare_fused(plan, wav_dev, n_rows, n_samples, row_stride, &p, &grid);
+  if (rc != DMEL_OK) return rc;
+  if (!logmel_dev) return fail(DMEL_ERR_INVALID, "logmel_dev is null");
+  if (n_rows == 0) return DMEL_OK;
+  p.logmel = logmel_dev;
+  DeviceGuard guard(plan->device);
+  DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream));
+  return DMEL_OK;
+}
+
+int dmel_minmax_f32(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
+                    long long row_stride, const int32_t* lengths_dev, float* min_dev, float* max_dev,
+                    void* stream) {
+  FusedParams p;
+  int grid = 0;
+  int rc = prepare_fused(plan, wav_dev, n_rows, n_samples, row_stride, &p, &grid);
+  if (rc != DMEL_OK) return rc;
+  if (!min_dev || !max_dev) return fail(DMEL_ERR_INVALID, "min_dev / max_dev is null");
+  if (n_rows == 0) return DMEL_OK;
+  p.lengths = lengths_dev;
+  p.run_min = min_dev;
+  p.run_max = max_dev;
+  DeviceGuard guard(plan->device);
+  DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream));
+  return DMEL_OK;
+}
+
+int dmel_encode_u8(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
+                   long long row_stride, const int32_t* lengths_dev, const float* lo_dev,
+                   const float* scale_dev, int n_bins, uint8_t* codes_dev, float* logmel_dev,
+                   unsigned long long* near_edge_dev, float edge_eps, void* stream) {
+  FusedParams p;
+  int grid = 0;
+  int rc = prepare_fused(plan, wav_dev, n_rows, n_samples, row_stride, &p, &grid);
+  if (rc != DMEL_OK) return rc;
+  if ((rc = check_bins(n_bins)) != DMEL_OK) return rc;
+  if (!lo_dev || !scale_dev || !codes_dev) return fail(DMEL_ERR_INVALID, "lo_dev / scale_dev / codes_dev is null");
+  if (n_rows == 0) return DMEL_OK;
+  p.lengths = lengths_dev;
+  p.q_lo = lo_dev;
+  p.q_scale = scale_dev;
+  p.n_bins = n_bins;
+  p.codes = codes_dev;
+  p.logmel = logmel_dev;
+  p.near_edge = near_edge_dev;
+  p.edge_eps = edge_eps;
+  DeviceGuard guard(plan->device);
+  DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream));
+  return DMEL_OK;
+}
+
+int dmel_encode_host_u8(dmel_plan* plan, const float* wav_host, long long n_rows, long long n_samples,
+                        long long row_stride, const int32_t* lengths_host, const float* lo_host,
+                        const float* scale_host, int n_bins, uint8_t* codes_host) {
+  if (!plan) return fail(DMEL_ERR_INVALID, "plan is null");
+  if (!wav_host || !codes_host || !lo_host || !scale_host)
+    return fail(DMEL_ERR_INVALID, "wav_host / codes_host / lo_host / scale_host is null");
+  int rc = check_bins(n_bins);
+  if (rc != DMEL_OK) return rc;
+  if (n_rows < 0 || n_samples <= 0 || row_stride < n_samples)
+    return fail(DMEL_ERR_INVALID, "bad waveform shape: rows=%lld samples=%lld stride=%lld", n_rows, n_samples, row_stride);
+  if (n_samples <= plan->pad_inner)
+    return fail(DMEL_ERR_INVALID, "reflect padding of %d needs more than %d samples per row, got %lld",
+                plan->pad_inner, plan->pad_inner, n_samples);
+  const long long T = num_frames(plan, n_samples);
+  if (T <= 0) return fail(DMEL_ERR_INVALID, "row of %lld samples is shorter than one frame", n_samples);
+  if (n_rows == 0) return DMEL_OK;
+  DeviceGuard guard(plan->device);
+  for (int i = 0; i < 2; ++i)
+    if (!plan->streams[i]) DMEL_CUDA(cudaStreamCreateWithFlags(&plan->streams[i], cudaStreamNonBlocking));
+  if (!plan->d_lo) {
+    DMEL_CUDA(cudaMalloc((void**)&plan->d_lo, plan->n_mels * sizeof(float)));
+    DMEL_CUDA(cudaMalloc((void**)&plan->d_scale, plan->n_mels * sizeof(float)));
+  }
+  // rows per chunk: about 16 MiB of waveform, so copies and kernels of neighbouring chunks overlap
+  const long long row_bytes = n_samples * 4;
+  long long chunk_rows = std::max<long long>(1, (16LL << 20) / row_bytes);
+  chunk_rows = std::min(chunk_rows, n_rows);
+  const size_t wav_need = (size_t)chunk_rows * n_samples;
+  const size_t codes_need = (size_t)chunk_rows * plan->n_mels * T;
+  if (wav_need > plan->wav_cap) {
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(plan->d_wav[i]);
+      plan->d_wav[i] = nullptr;
+      DMEL_CUDA(cudaMalloc((void**)&plan->d_wav[i], wav_need * sizeof(float)));
+    }
+    plan->wav_cap = wav_need;
+  }
+  if (codes_need > plan->codes_cap) {
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(plan->d_codes[i]);
+      plan->d_codes[i] = nullptr;
+      DMEL_CUDA(cudaMalloc((void**)&plan->d_codes[i], codes_need));
+    }
+    plan->codes_cap = codes_need;
+  }
+  if ((size_t)chunk_rows > plan->len_cap) {
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(plan->d_len[i]);
+      plan->d_len[i] = nullptr;
+      DMEL_CUDA(cudaMalloc((void**)&plan->d_len[i], chunk_rows * sizeof(int32_t)));
+    }
+    plan->len_cap = chunk_rows;
+  }
+  DMEL_CUDA(cudaMemcpyAsync(plan->d_lo, lo_host, plan->n_mels * sizeof(float), cudaMemcpyHostToDevice, plan->streams[0]));
+  DMEL_CUDA(cudaMemcpyAsync(plan->d_scale, scale_host, plan->n_mels * sizeof(float), cudaMemcpyHostToDevice, plan->streams[0]));
+  DMEL_CUDA(cudaStreamSynchronize(plan->streams[0]));
+  int slot = 0;
+  for (long long r0 = 0; r0 < n_rows; r0 += chunk_rows, slot ^= 1) {
+    const long long rows = std::min(chunk_rows, n_rows - r0);
+    cudaStream_t st = plan->streams[slot];
+    // stream order already guarantees the slot's previous D2H finished before this H2D starts
+    DMEL_CUDA(cudaMemcpy2DAsync(plan->d_wav[slot], n_samples * 4, wav_host + r0 * row_stride, row_stride * 4,
+                                n_samples * 4, rows, cudaMemcpyHostToDevice, st));
+    const int32_t* len_dev = nullptr;
+    if (lengths_host) {
+      DMEL_CUDA(cudaMemcpyAsync(plan->d_len[slot], lengths_host + r0, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      len_dev = plan->d_len[slot];
+    }
+    rc = dmel_encode_u8(plan, plan->d_wav[slot], rows, n_samples, n_samples, len_dev, plan->d_lo, plan->d_scale,
+                        n_bins, plan->d_codes[slot], nullptr, nullptr, 0.f, st);
+    if (rc != DMEL_OK) return rc;
+    DMEL_CUDA(cudaMemcpyAsync(codes_host + (size_t)r0 * plan->n_mels * T, plan->d_codes[slot],
+                              (size_t)rows * plan->n_mels * T, cudaMemcpyDeviceToHost, st));
+  }
+  DMEL_CUDA(cudaStreamSynchronize(plan->streams[0]));
+  DMEL_CUDA(cudaStreamSynchronize(plan->streams[1]));
+  return DMEL_OK;
+}
+
+static int check_tensor(const void* a, const void* b, long long n_rows, int n_mels, long long n_frames,
+                        unsigned* n_elems) {
+  if (!a || !b) return fail(DMEL_ERR_INVALID, "tensor pointer is null");
+  if (n_rows < 0 || n_mels < 1 || n_frames < 1)
+    return fail(DMEL_ERR_INVALID, "bad tensor shape (%lld, %d, %lld)", n_rows, n_mels, n_frames);
+  const long long n = n_rows * (long long)n_mels * n_frames;
+  if (n >= (1LL << 32) - 4096) return fail(DMEL_ERR_INVALID, "tensor of %lld elements exceeds the 2^32 flat-index limit; split the batch", n);
+  *n_elems = (unsigned)n;
+  return DMEL_OK;
+}
+
+int dmel_quantize_u8(const float* logmel_dev, long long n_rows, int n_mels, long long n_frames,
+                     const float* lo_dev, const float* scale_dev, int n_bins, uint8_t* codes_dev,
+                     void* stream) {
+  unsigned n = 0;
+  int rc = check_tensor(logmel_dev, codes_dev, n_rows, n_mels, n_frames, &n);
+  if (rc != DMEL_OK) return rc;
+  if ((rc = check_bins(n_bins)) != DMEL_OK) return rc;
+  if (!lo_dev || !scale_dev) return fail(DMEL_ERR_INVALID, "lo_dev / scale_dev is null");
+  if (n == 0) return DMEL_OK;
+  const bool vec = ((reinterpret_cast<uintptr_t>(logmel_dev) & 15) == 0) && ((reinterpret_cast<uintptr_t>(codes_dev) & 3) == 0);
+  dmel::quantize_kernel<<<stream_grid(nullptr, n >> 2), dmel::kStreamThreads, 0, (cudaStream_t)stream>>>(
+      logmel_dev, codes_dev, lo_dev, scale_dev, n, (unsigned)n_frames, (unsigned)n_mels, (unsigned)n_bins, vec);
+  DMEL_CUDA(cudaGetLastError());
+  return DMEL_OK;
+}
+
+int dmel_dequantize_f32(const uint8_t* codes_dev, long long n_rows, int n_mels, long long n_frames,
+                        const float* table_dev, int n_bins, float* logmel_dev, void* stream) {
+  unsigned n = 0;
+  int rc = check_tensor(codes_dev, logmel_dev, n_rows, n_mels, n_frames, &n);
+  if (rc != DMEL_OK) return rc;
+  if ((rc = check_bins(n_bins)) != DMEL_OK) return rc;
+  if (!table_dev) return fail(DMEL_ERR_INVALID, "table_dev is null");
+  if (n == 0) return DMEL_OK;
+  const bool vec = ((reinterpret_cast<uintptr_t>(logmel_dev) & 15) == 0) && ((reinterpret_cast<uintptr_t>(codes_dev) & 3) == 0);
+  dmel::dequantize_kernel<<<stream_grid(nullptr, n >> 2), dmel::kStreamThreads, 0, (cudaStream_t)stream>>>(
+      codes_dev, logmel_dev, table_dev, n, (unsigned)n_frames, (unsigned)n_mels, (unsigned)n_bins, vec);
+  DMEL_CUDA(cudaGetLastError());
+  return DMEL_OK;
+}
+
+int dmel_tensor_minmax_f32(const float* logmel_dev, long long n_rows, int n_mels, long long n_frames,
+                           const int32_t* n_valid_dev, float* min_dev, float* max_dev, void* stream) {
+  unsigned n = 0;
+  int rc = check_tensor(logmel_dev, min_dev, n_rows, n_mels, n_frames, &n);
+  if (rc != DMEL_OK) return rc;
+  if (!max_dev) return fail(DMEL_ERR_INVALID, "max_dev is null");
+  if (n == 0) return DMEL_OK;
+  const unsigned lines = (unsigned)(n_rows * n_mels);
+  const int blocks = (int)std::min<unsigned>((lines + 7) / 8, 148u * 8u);
+  dmel::tensor_minmax_kernel<<<blocks, dmel::kStreamThreads, 0, (cudaStream_t)stream>>>(
+      logmel_dev, n_valid_dev, min_dev, max_dev, lines, (unsigned)n_frames, (unsigned)n_mels);
+  DMEL_CUDA(cudaGetLastError());
+  return DMEL_OK;
+}
+
+}  // extern "C"

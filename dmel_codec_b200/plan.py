@@ -1,0 +1,216 @@
+"""Python handle on a native ``dmel_plan`` plus the tensor-level call wrappers.
+
+A plan fixes the transform geometry (n_fft, hop, mel filterbank, window) on one
+GPU.  The wrappers only do what torch is here for: allocate outputs, hand over
+raw device pointers and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native, filters
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} must be a CUDA tensor: dmel_codec_b200 runs on the GPU only (no CPU fallback); got device {t.device}")
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def as_rows(wav: torch.Tensor) -> torch.Tensor:
+    """(B, L) or (B, 1, L) -> (B, L) float32 with unit stride along L, the two
+    input layouts the reference accepts (utils/spectrogram.py:60-62)."""
+    if wav.ndim == 3:
+        if wav.shape[1] != 1:
+            raise ValueError(f"expected mono audio (B, 1, L), got {tuple(wav.shape)}")
+        wav = wav[:, 0, :]
+    elif wav.ndim != 2:
+        raise ValueError(f"expected audio of shape (B, L) or (B, 1, L), got {tuple(wav.shape)}")
+    if wav.dtype != torch.float32:
+        wav = wav.float()
+    if wav.shape[0] > 1 and (wav.stride(1) != 1 or wav.stride(0) < wav.shape[1]):
+        wav = wav.contiguous()
+    elif wav.stride(1) != 1:
+        wav = wav.contiguous()
+    return wav
+
+
+class Plan:
+    def __init__(self, *, sample_rate: int, n_fft: int, win_length: int, hop_length: int, n_mels: int,
+                 f_min: float = 0.0, f_max: Optional[float] = None, center: bool = False,
+                 device: torch.device | str | int = "cuda"):
+        self._handle = ctypes.c_void_p()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(f"dmel_codec_b200 plans live on CUDA devices only, got {self.device}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n_fft, self.hop_length, self.n_mels, self.center = int(n_fft), int(hop_length), int(n_mels), bool(center)
+        self.mel_basis = np.ascontiguousarray(
+            filters.mel_filterbank(sample_rate, n_fft, n_mels, f_min, f_max), dtype=np.float32)
+        self.window = np.ascontiguousarray(filters.stft_window(win_length, n_fft), dtype=np.float32)
+        lib = _native.load()
+        with torch.cuda.device(self.device):
+            _native.check(lib.dmel_plan_create(
+                self.n_fft, self.hop_length, self.n_mels, int(self.center),
+                self.mel_basis.ctypes.data_as(ctypes.c_void_p), self.window.ctypes.data_as(ctypes.c_void_p),
+                ctypes.byref(self._handle)))
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                _native.load().dmel_plan_destroy(h)
+            except Exception:
+                pass
+            self._handle = ctypes.c_void_p()
+
+    def num_frames(self, n_samples: int) -> int:
+        return int(_native.load().dmel_plan_num_frames(self._handle, int(n_samples)))
+
+    # -- waveform -> log-mel ------------------------------------------------
+    def logmel(self, wav: torch.Tensor) -> torch.Tensor:
+        _require_cuda(wav, "audio")
+        rows = as_rows(wav)
+        b, n = rows.shape
+        t = self._frames_or_raise(n)
+        out = torch.empty((b, self.n_mels, t), dtype=torch.float32, device=rows.device)
+        _native.check(_native.load().dmel_logmel_f32(
+            self._handle, rows.data_ptr(), b, n, rows.stride(0) if b > 1 else n, out.data_ptr(),
+            _stream_ptr(rows.device)))
+        return out
+
+    # -- calibration pass ---------------------------------------------------
+    def update_minmax(self, wav: torch.Tensor, lengths: Optional[torch.Tensor], run_min: torch.Tensor,
+                      run_max: torch.Tensor) -> None:
+        _require_cuda(wav, "audio")
+        rows = as_rows(wav)
+        b, n = rows.shape
+        self._frames_or_raise(n)
+        len_ptr = self._lengths_ptr(lengths, b, rows.device)
+        _native.check(_native.load().dmel_minmax_f32(
+            self._handle, rows.data_ptr(), b, n, rows.stride(0) if b > 1 else n, len_ptr[0],
+            run_min.data_ptr(), run_max.data_ptr(), _stream_ptr(rows.device)))
+
+    # -- waveform -> codes, fused --------------------------------------------
+    def encode(self, wav: torch.Tensor, lengths: Optional[torch.Tensor], lo: torch.Tensor, scale: torch.Tensor,
+               n_bins: int, *, return_logmel: bool = False, near_edge: Optional[torch.Tensor] = None,
+               edge_eps: float = 0.0):
+        _require_cuda(wav, "audio")
+        rows = as_rows(wav)
+        b, n = rows.shape
+        t = self._frames_or_raise(n)
+        codes = torch.empty((b, self.n_mels, t), dtype=torch.uint8, device=rows.device)
+        logmel = torch.empty((b, self.n_mels, t), dtype=torch.float32, device=rows.device) if return_logmel else None
+        len_ptr = self._lengths_ptr(lengths, b, rows.device)
+        _native.check(_native.load().dmel_encode_u8(
+            self._handle, rows.data_ptr(), b, n, rows.stride(0) if b > 1 else n, len_ptr[0],
+            lo.data_ptr(), scale.data_ptr(), int(n_bins), codes.data_ptr(),
+            logmel.data_ptr() if logmel is not None else None,
+            near_edge.data_ptr() if near_edge is not None else None, float(edge_eps),
+            _stream_ptr(rows.device)))
+        return (codes, logmel) if return_logmel else codes
+
+    def encode_host(self, wav: torch.Tensor, lengths: Optional[torch.Tensor], lo: torch.Tensor,
+                    scale: torch.Tensor, n_bins: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host tensors in, host tensor out; copies and kernels are pipelined
+        inside the library (``dmel_encode_host_u8``)."""
+        if wav.is_cuda:
+            raise ValueError("encode_host takes CPU tensors; use encode() for CUDA tensors")
+        rows = as_rows(wav)
+        b, n = rows.shape
+        t = self._frames_or_raise(n)
+        if out is None:
+            out = torch.empty((b, self.n_mels, t), dtype=torch.uint8, pin_memory=True)
+        lo_h = lo.detach().to("cpu", torch.float32).contiguous()
+        sc_h = scale.detach().to("cpu", torch.float32).contiguous()
+        len_h = None
+        if lengths is not None:
+            len_h = lengths.detach().to("cpu", torch.int32).reshape(-1).contiguous()
+            if len_h.numel() != b:
+                raise ValueError(f"lengths has {len_h.numel()} entries for a batch of {b}")
+        with torch.cuda.device(self.device):
+            _native.check(_native.load().dmel_encode_host_u8(
+                self._handle, rows.data_ptr(), b, n, rows.stride(0) if b > 1 else n,
+                len_h.data_ptr() if len_h is not None else None, lo_h.data_ptr(), sc_h.data_ptr(),
+                int(n_bins), out.data_ptr()))
+        return out
+
+    # -- helpers --------------------------------------------------------------
+    def _frames_or_raise(self, n_samples: int) -> int:
+        pad = (self.n_fft - self.hop_length) // 2
+        if n_samples <= pad:
+            raise ValueError(
+                f"reflect padding of {pad} needs more than {pad} samples per row, got {n_samples}")
+        t = self.num_frames(n_samples)
+        if t <= 0:
+            raise ValueError(f"{n_samples} samples are shorter than one frame of {self.n_fft}")
+        return t
+
+    def _lengths_ptr(self, lengths: Optional[torch.Tensor], b: int, device: torch.device):
+        """Returns (pointer-or-None, keepalive)."""
+        if lengths is None:
+            return None, None
+        flat = lengths.reshape(-1)
+        if flat.numel() != b:
+            raise ValueError(f"lengths has {flat.numel()} entries for a batch of {b}")
+        flat = flat.to(device=device, dtype=torch.int32).contiguous()
+        self._len_keepalive = flat  # stays alive until the next call on this plan
+        return flat.data_ptr(), flat
+
+
+# ---------------------------------------------------------------------------
+# tensor-level quantiser stages (no plan needed)
+# ---------------------------------------------------------------------------
+def quantize(mel: torch.Tensor, lo: torch.Tensor, scale: torch.Tensor, n_bins: int) -> torch.Tensor:
+    _require_cuda(mel, "mel")
+    if mel.ndim != 3:
+        raise ValueError(f"expected (B, n_mels, T), got {tuple(mel.shape)}")
+    x = mel.float().contiguous()
+    b, m, t = x.shape
+    codes = torch.empty((b, m, t), dtype=torch.uint8, device=x.device)
+    if x.numel():
+        _native.check(_native.load().dmel_quantize_u8(
+            x.data_ptr(), b, m, t, lo.data_ptr(), scale.data_ptr(), int(n_bins), codes.data_ptr(),
+            _stream_ptr(x.device)))
+    return codes
+
+
+def dequantize(codes: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    _require_cuda(codes, "codes")
+    if codes.ndim != 3 or codes.dtype != torch.uint8:
+        raise ValueError(f"expected uint8 codes (B, n_mels, T), got {codes.dtype} {tuple(codes.shape)}")
+    c = codes.contiguous()
+    b, m, t = c.shape
+    if table.shape[0] != m:
+        raise ValueError(f"codes have {m} channels, the quantiser has {table.shape[0]}")
+    out = torch.empty((b, m, t), dtype=torch.float32, device=c.device)
+    if c.numel():
+        _native.check(_native.load().dmel_dequantize_f32(
+            c.data_ptr(), b, m, t, table.data_ptr(), int(table.shape[1]), out.data_ptr(),
+            _stream_ptr(c.device)))
+    return out
+
+
+def tensor_minmax(mel: torch.Tensor, n_valid: Optional[torch.Tensor], run_min: torch.Tensor,
+                  run_max: torch.Tensor) -> None:
+    _require_cuda(mel, "mel")
+    x = mel.float().contiguous()
+    b, m, t = x.shape
+    nv = None
+    if n_valid is not None:
+        nv = n_valid.reshape(-1).to(device=x.device, dtype=torch.int32).contiguous()
+        if nv.numel() != b:
+            raise ValueError(f"n_valid has {nv.numel()} entries for a batch of {b}")
+    if x.numel():
+        _native.check(_native.load().dmel_tensor_minmax_f32(
+            x.data_ptr(), b, m, t, nv.data_ptr() if nv is not None else None, run_min.data_ptr(),
+            run_max.data_ptr(), _stream_ptr(x.device)))

@@ -1,0 +1,223 @@
+"""dMel bin quantiser, dequantiser and calibration.
+
+The reference ships no such module — its quantiser is the learned
+``DownsampleFiniteScalarQuantize`` (reference models/modules/dowmsample_fsq.py)
+— so the arithmetic here is this repo's own spec.  The *API shape* mirrors that
+reference class so a codec that swaps quantisers keeps its call sites:
+``encode(z) -> codes``, ``decode(codes) -> z`` and ``forward(z) ->
+Result(z, codes, latents)`` (dowmsample_fsq.py:12-16, :86, :124, :135), and
+``DMelTokenizer.encode(audios, audio_lengths) -> (codes, code_lengths)`` mirrors
+``VQGAN.encode`` (reference models/codec_lit_modules.py:462-466).
+
+Per mel channel c with calibrated [lo_c, hi_c] and K bins, float32:
+
+    code  = clamp(floor((x - lo_c) * (K / (hi_c - lo_c))), 0, K - 1)   uint8
+    x_hat = lo_c + (code + 0.5) * ((hi_c - lo_c) / K)
+
+Calibration is the per-channel min / max of log-mel over all valid frames
+(t < audio_length // hop, the caller's mask rule at codec_lit_modules.py:176);
+min and max are exact and order independent, so sharded calibration followed
+by an all-reduce is bit-identical to a single-GPU pass.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Iterable, Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import plan as _plan
+from .spectrogram import LogMelSpectrogram
+
+
+@dataclass
+class DMelResult:
+    z: Tensor        # dequantised log-mel (B, n_mels, T) float32
+    codes: Tensor    # (B, n_mels, T) uint8
+    latents: Tensor  # the input log-mel
+
+
+class DMelQuantizer(nn.Module):
+    def __init__(self, n_mels: int, n_bins: int = 16):
+        super().__init__()
+        if not 1 <= n_bins <= 256:
+            raise ValueError("n_bins must be in [1, 256] (codes are uint8)")
+        self.n_mels = int(n_mels)
+        self.n_bins = int(n_bins)
+        # registered so calibration survives checkpoints
+        self.register_buffer("lo", torch.full((n_mels,), float("inf"), dtype=torch.float32))
+        self.register_buffer("hi", torch.full((n_mels,), float("-inf"), dtype=torch.float32))
+        # derived tensors (scale, table, "is calibrated") are cached until the stats change,
+        # so the steady-state encode path issues no extra kernels and no host sync
+        self._derived = {}
+
+    def _invalidate(self) -> None:
+        self._derived = {}
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() move the buffers
+        self._invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._invalidate()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    # -- statistics -----------------------------------------------------------
+    @property
+    def calibrated(self) -> bool:
+        if "ready" not in self._derived:
+            self._derived["ready"] = bool(torch.all(self.lo <= self.hi).item())
+        return self._derived["ready"]
+
+    def reset_stats(self) -> None:
+        self._invalidate()
+        self.lo.fill_(float("inf"))
+        self.hi.fill_(float("-inf"))
+
+    def set_stats(self, lo: Tensor, hi: Tensor) -> None:
+        self._invalidate()
+        self.lo.copy_(lo.to(self.lo))
+        self.hi.copy_(hi.to(self.hi))
+
+    @torch.no_grad()
+    def update_stats(self, mel: Tensor, mel_lengths: Optional[Tensor] = None) -> None:
+        """Fold the min / max of a (B, n_mels, T) log-mel batch into lo / hi;
+        frames at or past ``mel_lengths[b]`` are ignored."""
+        self._check_channels(mel)
+        self._invalidate()
+        _plan.tensor_minmax(mel, mel_lengths, self.lo, self.hi)
+
+    @torch.no_grad()
+    def sync_stats(self, group=None) -> None:
+        """All-reduce lo (MIN) and hi (MAX) across ranks: the one collective of
+        the whole path (2 * n_mels floats, NCCL over NVLink when on GPUs)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        self._invalidate()
+        dist.all_reduce(self.lo, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(self.hi, op=dist.ReduceOp.MAX, group=group)
+
+    def scale(self) -> Tensor:
+        """K / (hi - lo) per channel, 0 where the channel is degenerate."""
+        if "scale" not in self._derived:
+            width = self.hi - self.lo
+            k = torch.tensor(float(self.n_bins), dtype=torch.float32, device=width.device)
+            self._derived["scale"] = torch.where(width > 0, k / width, torch.zeros_like(width))
+        return self._derived["scale"]
+
+    def table(self) -> Tensor:
+        """(n_mels, K) bin centres, separate multiply and add (no FMA)."""
+        if "table" not in self._derived:
+            step = (self.hi - self.lo) / float(self.n_bins)
+            k = torch.arange(self.n_bins, dtype=torch.float32, device=step.device) + 0.5
+            prod = k[None, :] * step[:, None]
+            self._derived["table"] = (self.lo[:, None] + prod).contiguous()
+        return self._derived["table"]
+
+    # -- codec API (names follow reference dowmsample_fsq.py:86/:124/:135) -----
+    @torch.no_grad()
+    def encode(self, z: Tensor) -> Tensor:
+        self._check_ready()
+        self._check_channels(z)
+        return _plan.quantize(z, self.lo, self.scale(), self.n_bins)
+
+    @torch.no_grad()
+    def decode(self, indices: Tensor) -> Tensor:
+        self._check_ready()
+        return _plan.dequantize(indices, self.table())
+
+    @torch.no_grad()
+    def forward(self, z: Tensor) -> DMelResult:
+        codes = self.encode(z)
+        return DMelResult(z=self.decode(codes), codes=codes, latents=z)
+
+    # -- helpers ----------------------------------------------------------------
+    def _check_ready(self) -> None:
+        if not self.calibrated:
+            raise RuntimeError("DMelQuantizer has no calibration: call update_stats()/calibrate() or set_stats() first")
+
+    def _check_channels(self, mel: Tensor) -> None:
+        if mel.ndim != 3 or mel.shape[1] != self.n_mels:
+            raise ValueError(f"expected (B, {self.n_mels}, T), got {tuple(mel.shape)}")
+
+
+class DMelTokenizer(nn.Module):
+    """waveform <-> dMel codes.  ``encode`` is the fused hot path: one kernel
+    reads float32 samples and writes uint8 codes; log-mel never reaches HBM."""
+
+    def __init__(self, sample_rate=44100, n_fft=2048, win_length=2048, hop_length=512, n_mels=128,
+                 n_bins=16, center=False, f_min=0.0, f_max=None):
+        super().__init__()
+        self.mel_transform = LogMelSpectrogram(sample_rate=sample_rate, n_fft=n_fft, win_length=win_length,
+                                               hop_length=hop_length, n_mels=n_mels, center=center,
+                                               f_min=f_min, f_max=f_max)
+        self.quantizer = DMelQuantizer(n_mels, n_bins)
+        self.hop_length = hop_length
+        self.sample_rate = sample_rate
+
+    def _plan(self, device: torch.device) -> _plan.Plan:
+        return self.mel_transform.spectrogram.plan_for(device)
+
+    @staticmethod
+    def _flat_lengths(audio_lengths: Optional[Tensor]) -> Optional[Tensor]:
+        # the reference data module yields audio_lengths as (1, B) int32
+        # (dataset/lhotse_tts_dataset.py:60-65); sequence_mask squeezes it
+        return None if audio_lengths is None else audio_lengths.reshape(-1)
+
+    # -- calibration ----------------------------------------------------------
+    @torch.no_grad()
+    def update_stats(self, audios: Tensor, audio_lengths: Optional[Tensor] = None) -> None:
+        """One calibration step on a batch of waveforms (fused: no log-mel tensor)."""
+        q = self.quantizer
+        q._invalidate()
+        self._plan(audios.device).update_minmax(audios, self._flat_lengths(audio_lengths), q.lo, q.hi)
+
+    @torch.no_grad()
+    def calibrate(self, batches: Iterable, group=None) -> Tuple[Tensor, Tensor]:
+        """Reset, scan ``batches`` (audios or (audios, audio_lengths)), then
+        all-reduce across ranks.  Returns (lo, hi)."""
+        self.quantizer.reset_stats()
+        for item in batches:
+            audios, lengths = (item if isinstance(item, (tuple, list)) else (item, None))
+            self.update_stats(audios, lengths)
+        self.quantizer.sync_stats(group)
+        return self.quantizer.lo, self.quantizer.hi
+
+    # -- codec API (reference VQGAN.encode / decode, codec_lit_modules.py:462-484)
+    @torch.no_grad()
+    def encode(self, audios: Tensor, audio_lengths: Optional[Tensor] = None, *, return_mel: bool = False,
+               near_edge: Optional[Tensor] = None, edge_eps: float = 0.0):
+        """-> (codes (B, n_mels, T) uint8, code_lengths or None[, log-mel])."""
+        q = self.quantizer
+        q._check_ready()
+        lengths = self._flat_lengths(audio_lengths)
+        out = self._plan(audios.device).encode(audios, lengths, q.lo, q.scale(), q.n_bins,
+                                               return_logmel=return_mel, near_edge=near_edge, edge_eps=edge_eps)
+        code_lengths = None if lengths is None else torch.div(lengths, self.hop_length, rounding_mode="floor")
+        if return_mel:
+            return out[0], code_lengths, out[1]
+        return out, code_lengths
+
+    @torch.no_grad()
+    def encode_host(self, audios: Tensor, audio_lengths: Optional[Tensor] = None,
+                    out: Optional[Tensor] = None) -> Tensor:
+        """CPU (ideally pinned) waveforms in, CPU codes out, transfers pipelined natively."""
+        q = self.quantizer
+        q._check_ready()
+        return self._plan(q.lo.device).encode_host(audios, self._flat_lengths(audio_lengths), q.lo, q.scale(),
+                                                   q.n_bins, out)
+
+    @torch.no_grad()
+    def decode(self, indices: Tensor, feature_lengths: Optional[Tensor] = None) -> Tensor:
+        """codes -> log-mel bin centres; frames past ``feature_lengths`` are zeroed
+        like the reference's masked decode (codec_lit_modules.py:468-476)."""
+        mel = self.quantizer.decode(indices)
+        if feature_lengths is not None:
+            t = torch.arange(mel.shape[2], device=mel.device)
+            mel = mel * (t[None, None, :] < feature_lengths.reshape(-1, 1, 1).to(mel.device))
+        return mel
+
+    def forward(self, audios: Tensor, audio_lengths: Optional[Tensor] = None):
+        return self.encode(audios, audio_lengths)

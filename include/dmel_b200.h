@@ -1,0 +1,116 @@
+/* dmel_b200.h — C ABI of the B200 dMel tokenization path.
+ *
+ * The reference (ishine/dmel_codec) has no FFI for this path: it is a Python
+ * nn.Module (dmel_codec/utils/spectrogram.py) calling torch ops.  These entry
+ * points are what a binding for that module would call instead; each one names
+ * the reference code it replaces.  No torch types cross this boundary: plain
+ * pointers, sizes and a CUDA stream handle.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative DMEL_ERR_* otherwise, and
+ *     never throws; dmel_last_error() gives the message for the calling thread;
+ *   - "dev" pointers are device memory on the plan's GPU, "host" pointers are
+ *     host memory; the library never allocates or frees caller tensors;
+ *   - work is queued on `stream` (a cudaStream_t passed as void*, NULL = the
+ *     legacy default stream) and the call returns without synchronising,
+ *     except the *_host_* functions, which return after the result is in the
+ *     caller's host buffer;
+ *   - tensors are dense row-major: waveforms (B, row_stride >= L) float32,
+ *     log-mel (B, n_mels, T) float32, codes (B, n_mels, T) uint8, with
+ *     T = dmel_plan_num_frames(plan, L).
+ */
+#ifndef DMEL_B200_H
+#define DMEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMEL_ABI_VERSION 1
+
+#define DMEL_OK 0
+#define DMEL_ERR_INVALID (-1)     /* bad argument (shape, null pointer, L <= reflect pad ...) */
+#define DMEL_ERR_UNSUPPORTED (-2) /* geometry this build has no kernel for */
+#define DMEL_ERR_CUDA (-3)        /* CUDA runtime error, text in dmel_last_error() */
+#define DMEL_ERR_NO_DEVICE (-4)   /* no CUDA device: there is no CPU fallback */
+
+typedef struct dmel_plan dmel_plan;
+
+int dmel_abi_version(void);
+const char* dmel_last_error(void);
+
+/* Geometry + constants of one transform.  Replaces the lazily cached
+ * mel_basis / hann_window of LinearSpectrogram.forward
+ * (reference dmel_codec/utils/spectrogram.py:43-56).
+ *   mel_basis_host : (n_mels, n_fft/2+1) float32, row-major  (librosa.filters.mel, :45-52)
+ *   window_host    : (n_fft) float32, already centre-padded if win_length < n_fft (:53)
+ *   center         : 0/1, the `center` flag handed to torch.stft (:70)
+ * The reflect pad (n_fft - hop)/2 of :58-62 is implied.  Supported n_fft: 1024, 2048.
+ * The plan binds to the CUDA device that is current at the time of the call. */
+int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center,
+                     const float* mel_basis_host, const float* window_host,
+                     dmel_plan** out);
+void dmel_plan_destroy(dmel_plan* plan);
+
+/* T for a row of n_samples (reference: shape of the torch.stft output, :64-75);
+ * <= 0 when the row is too short.  n_samples must exceed the reflect pad. */
+long long dmel_plan_num_frames(const dmel_plan* plan, long long n_samples);
+
+/* waveform -> log-mel.  Replaces LinearSpectrogram.forward
+ * (reference dmel_codec/utils/spectrogram.py:41-81). */
+int dmel_logmel_f32(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
+                    long long row_stride, float* logmel_dev, void* stream);
+
+/* Calibration pass: running per-channel min / max of the log-mel of this batch
+ * over valid frames (t < lengths[b] / hop; lengths_dev may be NULL = all T).
+ * min_dev / max_dev (n_mels) are UPDATED in place (initialise to +inf / -inf),
+ * so batches and ranks compose.  Not in the reference;
+ * valid-frame rule from reference models/codec_lit_modules.py:176-177. */
+int dmel_minmax_f32(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
+                    long long row_stride, const int32_t* lengths_dev,
+                    float* min_dev, float* max_dev, void* stream);
+
+/* waveform -> uint8 dMel codes, fused.  code = clamp(floor((x - lo_c) * scale_c), 0, K-1)
+ * with scale_c = K / (hi_c - lo_c) supplied by the caller (float32, n_mels each).
+ * Frames at or past lengths[b] / hop get code 0.  Optional outputs (NULL to skip):
+ *   logmel_dev     : (B, n_mels, T) the pre-quantisation values
+ *   near_edge_dev  : one uint64, incremented by the number of valid values closer
+ *                    than edge_eps (log-mel units) to an interior bin edge.
+ * Stands where the reference calls encode_mel_transform then quantises
+ * (reference models/codec_lit_modules.py:486-513). */
+int dmel_encode_u8(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
+                   long long row_stride, const int32_t* lengths_dev,
+                   const float* lo_dev, const float* scale_dev, int n_bins,
+                   uint8_t* codes_dev, float* logmel_dev,
+                   unsigned long long* near_edge_dev, float edge_eps, void* stream);
+
+/* Same as dmel_encode_u8 with HOST buffers: chunks rows through pinned staging,
+ * overlapping H2D, kernel and D2H on internal streams; returns when codes_host
+ * is complete.  lengths_host may be NULL; lo/scale are host arrays too. */
+int dmel_encode_host_u8(dmel_plan* plan, const float* wav_host, long long n_rows, long long n_samples,
+                        long long row_stride, const int32_t* lengths_host,
+                        const float* lo_host, const float* scale_host, int n_bins,
+                        uint8_t* codes_host);
+
+/* Stand-alone quantiser stages on an existing (B, n_mels, T) log-mel tensor. */
+int dmel_quantize_u8(const float* logmel_dev, long long n_rows, int n_mels, long long n_frames,
+                     const float* lo_dev, const float* scale_dev, int n_bins,
+                     uint8_t* codes_dev, void* stream);
+
+/* codes -> bin-centre log-mel.  table_dev is (n_mels, n_bins) float32:
+ * table[c][k] = lo_c + (k + 0.5) * (hi_c - lo_c) / K.  Codes >= n_bins read as n_bins-1. */
+int dmel_dequantize_f32(const uint8_t* codes_dev, long long n_rows, int n_mels, long long n_frames,
+                        const float* table_dev, int n_bins, float* logmel_dev, void* stream);
+
+/* Running min/max over valid frames of an existing log-mel tensor
+ * (n_valid_dev: frames per row, or NULL). Updates min_dev / max_dev in place. */
+int dmel_tensor_minmax_f32(const float* logmel_dev, long long n_rows, int n_mels, long long n_frames,
+                           const int32_t* n_valid_dev, float* min_dev, float* max_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMEL_B200_H */
