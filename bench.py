@@ -206,21 +206,23 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     total_ms, enc_total, deq_total, wall_ms = t.tolist()
 
     # ---- end to end through the public API with HOST buffers -------------------
-    host = [ring[r].cpu().pin_memory() for r in range(2)]
-    out = torch.empty((BATCH, GEOM["n_mels"], N_FRAMES), dtype=torch.uint8).pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
-    for r in range(2):
-        tok.encode_host(host[r], out=out)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        tok.encode_host(host[i % 2], out=out)  # returns after codes are in host memory
-    e2e_dt = time.perf_counter() - t0
-    e = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e, op=dist.ReduceOp.MAX)
-    e2e_value = world * AUDIO_SEC_PER_BATCH * e2e_steps / e.item()
+    e2e_value = None
+    if not args.skip_e2e:
+        host = [ring[r].cpu().pin_memory() for r in range(2)]
+        out = torch.empty((BATCH, GEOM["n_mels"], N_FRAMES), dtype=torch.uint8).pin_memory()
+        for r in range(2):
+            tok.encode_host(host[r], out=out)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            tok.encode_host(host[i % 2], out=out)  # returns after codes are in host memory
+        e2e_dt = time.perf_counter() - t0
+        e = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        e2e_value = world * AUDIO_SEC_PER_BATCH * e2e_steps / e.item()
 
     if rank != 0:
         return
@@ -236,15 +238,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     # CPU baseline: the oracle port on this box's host cores, bounded sample
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cwav, cfg, bank, clo, chi = cpu_oracle_setup(BATCH)
-    oracle_step(cwav, cfg, bank, clo, chi)
-    passes, c0 = 0, time.perf_counter()
-    while passes < 3 or (time.perf_counter() - c0 < 10.0 and passes < 200):
+    cpu_value, passes, cpu_dt = None, 0, 0.0
+    if not args.skip_cpu:
+        torch.set_num_threads(cores)
+        cwav, cfg, bank, clo, chi = cpu_oracle_setup(BATCH)
         oracle_step(cwav, cfg, bank, clo, chi)
-        passes += 1
-    cpu_dt = time.perf_counter() - c0
-    cpu_value = AUDIO_SEC_PER_BATCH * passes / cpu_dt
+        c0 = time.perf_counter()
+        while passes < 3 or (time.perf_counter() - c0 < 10.0 and passes < 200):
+            oracle_step(cwav, cfg, bank, clo, chi)
+            passes += 1
+        cpu_dt = time.perf_counter() - c0
+        cpu_value = AUDIO_SEC_PER_BATCH * passes / cpu_dt
 
     value = world * AUDIO_SEC_PER_BATCH * args.steps / (total_ms / 1e3)
     print(json.dumps({
@@ -275,6 +279,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: leave out the CPU-baseline leg")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: leave out the host-buffer leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
