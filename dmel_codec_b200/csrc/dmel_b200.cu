@@ -55,6 +55,7 @@ struct dmel_plan {
   int n_fft = 0, hop = 0, n_mels = 0, center = 0;
   int pad_inner = 0, pad_outer = 0;
   int tile_frames = 0;  // TF chosen for this geometry
+  int ctas_per_sm = 1;
   int wave_len = 0;
   int nnz = 0;
   size_t smem_bytes = 0;
@@ -83,35 +84,43 @@ size_t fused_smem(int wave_len, int n_mels, int nnz) {
 }
 
 size_t fused_smem_for(int n_fft, int tf, int wave_len, int n_mels, int nnz) {
-  if (n_fft == 1024) {
-    if (tf == 32) return fused_smem<1024, 32>(wave_len, n_mels, nnz);
-    if (tf == 16) return fused_smem<1024, 16>(wave_len, n_mels, nnz);
-    return fused_smem<1024, 8>(wave_len, n_mels, nnz);
-  }
-  if (tf == 32) return fused_smem<2048, 32>(wave_len, n_mels, nnz);
-  if (tf == 16) return fused_smem<2048, 16>(wave_len, n_mels, nnz);
-  return fused_smem<2048, 8>(wave_len, n_mels, nnz);
+  if (n_fft == 1024) return tf == 16 ? fused_smem<1024, 16>(wave_len, n_mels, nnz) : fused_smem<1024, 8>(wave_len, n_mels, nnz);
+  return tf == 16 ? fused_smem<2048, 16>(wave_len, n_mels, nnz) : fused_smem<2048, 8>(wave_len, n_mels, nnz);
 }
 
-template <int NFFT, int TF>
+template <int NFFT, int TF, int MODE>
 cudaError_t launch_fused(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st) {
-  auto kern = dmel::dmel_fused_kernel<NFFT, TF>;
+  auto kern = dmel::dmel_fused_kernel<NFFT, TF, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
   if (e != cudaSuccess) return e;
   kern<<<grid, dmel::kThreads, plan->smem_bytes, st>>>(p);
   return cudaGetLastError();
 }
 
-cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st) {
+template <int MODE>
+cudaError_t launch_fused_mode(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st) {
   const int tf = plan->tile_frames;
-  if (plan->n_fft == 1024) {
-    if (tf == 32) return launch_fused<1024, 32>(plan, p, grid, st);
-    if (tf == 16) return launch_fused<1024, 16>(plan, p, grid, st);
-    return launch_fused<1024, 8>(plan, p, grid, st);
+  if (plan->n_fft == 1024)
+    return tf == 16 ? launch_fused<1024, 16, MODE>(plan, p, grid, st) : launch_fused<1024, 8, MODE>(plan, p, grid, st);
+  return tf == 16 ? launch_fused<2048, 16, MODE>(plan, p, grid, st) : launch_fused<2048, 8, MODE>(plan, p, grid, st);
+}
+
+cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st) {
+  using namespace dmel;
+  int mode = 0;
+  if (p.codes) mode |= kOutCodes;
+  if (p.logmel) mode |= kOutLogmel;
+  if (p.run_min) mode |= kOutStats;
+  if (p.near_edge) mode |= kOutEdge;
+  switch (mode) {
+    case kOutCodes: return launch_fused_mode<kOutCodes>(plan, p, grid, st);
+    case kOutLogmel: return launch_fused_mode<kOutLogmel>(plan, p, grid, st);
+    case kOutStats: return launch_fused_mode<kOutStats>(plan, p, grid, st);
+    case kOutCodes | kOutLogmel: return launch_fused_mode<kOutCodes | kOutLogmel>(plan, p, grid, st);
+    case kOutCodes | kOutEdge: return launch_fused_mode<kOutCodes | kOutEdge>(plan, p, grid, st);
+    case kOutCodes | kOutLogmel | kOutEdge: return launch_fused_mode<kOutCodes | kOutLogmel | kOutEdge>(plan, p, grid, st);
+    default: return cudaErrorInvalidValue;
   }
-  if (tf == 32) return launch_fused<2048, 32>(plan, p, grid, st);
-  if (tf == 16) return launch_fused<2048, 16>(plan, p, grid, st);
-  return launch_fused<2048, 8>(plan, p, grid, st);
 }
 
 long long num_frames(const dmel_plan* plan, long long n_samples) {
@@ -159,7 +168,7 @@ int prepare_fused(dmel_plan* plan, const float* wav, long long n_rows, long long
   p->chan = plan->d_chan;
   p->weights = plan->d_weights;
   p->n_bins = 1;
-  *grid = (int)std::min<long long>(n_tiles, plan->sm_count);
+  *grid = (int)std::min<long long>(n_tiles, (long long)plan->sm_count * plan->ctas_per_sm);
   return DMEL_OK;
 }
 
@@ -248,18 +257,25 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
   }
   plan->nnz = (int)weights.size();
 
-  // largest frame tile whose shared-memory footprint fits
-  const int candidates[3] = {32, 16, 8};
-  for (int tf : candidates) {
-    const int wave_len = ((tf - 1) * hop_length + n_fft + 3) / 4 * 4;
-    const size_t need = fused_smem_for(n_fft, tf, wave_len, n_mels, plan->nnz);
-    if (need <= (size_t)plan->max_smem) {
-      plan->tile_frames = tf;
-      plan->wave_len = wave_len;
-      plan->smem_bytes = need;
-      break;
+  // frame tile: prefer one that lets two CTAs share an SM (n_fft 1024 kernels are built for
+  // 128 registers / 2 CTAs), else the largest that fits at all
+  int max_sm_smem = 0;
+  DMEL_CUDA(cudaDeviceGetAttribute(&max_sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, plan->device));
+  const size_t half_sm = (size_t)max_sm_smem / 2 - 1024;  // 1 KB per CTA is reserved by the driver
+  const int candidates[2] = {16, 8};
+  for (int pass = 0; pass < 2 && !plan->tile_frames; ++pass)
+    for (int tf : candidates) {
+      const int wave_len = ((tf - 1) * hop_length + n_fft + 3) / 4 * 4;
+      const size_t need = fused_smem_for(n_fft, tf, wave_len, n_mels, plan->nnz);
+      const size_t limit = (pass == 0 && n_fft == 1024) ? half_sm : (size_t)plan->max_smem;
+      if (need <= limit) {
+        plan->tile_frames = tf;
+        plan->wave_len = wave_len;
+        plan->smem_bytes = need;
+        plan->ctas_per_sm = (n_fft == 1024 && need <= half_sm) ? 2 : 1;
+        break;
+      }
     }
-  }
   if (!plan->tile_frames) {
     const int max_smem = plan->max_smem;
     delete plan;
@@ -267,15 +283,17 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
   }
 
   std::vector<float> window(window_host, window_host + n_fft);
-  std::vector<float2> stage_tw(32 * 32), fold_tw(513);
+  // inter-pass twiddles W_C^{k1*n2} (C = n_fft/2 complex points, n2 = lane) and unfold twiddles W_{n_fft}^k
+  const int n_complex = n_fft / 2, rows = n_complex / 32;
+  std::vector<float2> stage_tw((size_t)rows * 32), fold_tw(n_fft / 4 + 1);
   const double two_pi = 6.283185307179586476925286766559;
-  for (int k1 = 0; k1 < 32; ++k1)
+  for (int k1 = 0; k1 < rows; ++k1)
     for (int n2 = 0; n2 < 32; ++n2) {
-      const double a = -two_pi * double((k1 * n2) % 1024) / 1024.0;
+      const double a = -two_pi * double((k1 * n2) % n_complex) / n_complex;
       stage_tw[k1 * 32 + n2] = make_float2((float)std::cos(a), (float)std::sin(a));
     }
-  for (int k = 0; k <= 512; ++k) {
-    const double a = -two_pi * double(k) / 2048.0;
+  for (int k = 0; k <= n_fft / 4; ++k) {
+    const double a = -two_pi * double(k) / n_fft;
     fold_tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
   }
   cudaError_t e = upload(&plan->d_window, window);

@@ -1,18 +1,23 @@
 // Register-resident FFT building blocks for the fused dMel kernel.
 //
-// A warp computes one 1024-point complex FFT as 32 x 32 (Cooley-Tukey, two
-// radix-32 passes).  Every lane keeps 32 complex points in registers, does a
-// fully unrolled radix-32 DFT on them, and the single 32x32 transpose between
-// the two passes goes through a padded shared-memory tile (one STS.64 sweep,
-// one LDS.128 sweep, both bank-conflict free).  Real input rides on that core
-// either as two frames packed into one complex signal (n_fft = 1024) or as one
-// frame folded to half length (n_fft = 2048); see logmel_kernel.cuh.
+// A real frame of n_fft samples is folded to n_fft/2 complex points
+// z[n] = x[2n] + i*x[2n+1]; one warp computes Z = FFT(z) in two register passes
+// around a single shared-memory transpose, then unfolds Z into the n_fft/2+1
+// magnitudes.  Every frame has its own FFT, so a quiet frame never inherits
+// rounding noise from a loud neighbour.
+//
+//   n_fft = 1024 : 512 = 16 x 32.  Pass 1: lane n2 does a radix-16 DFT over
+//                  n1 (16 points in registers).  Pass 2: the 32-point DFT of
+//                  row k1 is shared by the lane pair (k1, k1+16): each lane a
+//                  radix-16 over one parity of n2, then one cross-lane radix-2.
+//   n_fft = 2048 : 1024 = 32 x 32, radix-32 in registers in both passes.
 //
 // Replaces, together with logmel_kernel.cuh, the torch.stft call at reference
-// dmel_codec/utils/spectrogram.py:64-75.
+// dmel_codec/utils/spectrogram.py:64-75 and the magnitude at :76.
 //
-// Everything here is __host__ __device__ so tests/host_emul.cu can run the same
-// code on the CPU, lane by lane, against a float64 DFT.
+// The arithmetic is __host__ __device__ and split at every cross-lane exchange,
+// so tests/host_emul.cu runs the same code on the CPU lane by lane against a
+// float64 DFT.
 #pragma once
 #include <cuda_runtime.h>
 #include <utility>
@@ -21,9 +26,11 @@ namespace dmel {
 
 #define DMEL_HD __host__ __device__ __forceinline__
 
-// bit reversal of a 5-bit index
 DMEL_HD constexpr int brev5(int x) {
   return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
+}
+DMEL_HD constexpr int brev4(int x) {
+  return ((x & 1) << 3) | ((x & 2) << 1) | ((x & 4) >> 1) | ((x & 8) >> 3);
 }
 
 // cos(2*pi*q/32) for q = 0..8, correctly rounded to float
@@ -68,67 +75,45 @@ DMEL_HD float2 mul_w32(float2 d) {
   }
 }
 
-// one decimation-in-frequency butterfly of span H, butterfly number I (0..15)
-template <int H, int I>
-DMEL_HD void dif_butterfly(float2 (&a)[32]) {
+// ---- radix-32 / radix-16 decimation-in-frequency butterflies ------------------
+template <int N, int H, int I>
+DMEL_HD void dif_butterfly(float2 (&a)[N]) {
   constexpr int blk = I / H, j = I % H;
   constexpr int p = blk * 2 * H + j, q = p + H;
   const float2 u = a[p], w = a[q];
   a[p] = cadd(u, w);
-  a[q] = mul_w32<j * (16 / H)>(csub(u, w));
+  a[q] = mul_w32<j * (16 / H)>(csub(u, w));  // W_{2H}^j == W_32^{j*16/H}
 }
-template <int H, int... I>
-DMEL_HD void dif_stage(float2 (&a)[32], std::integer_sequence<int, I...>) {
-  (dif_butterfly<H, I>(a), ...);
+template <int N, int H, int... I>
+DMEL_HD void dif_stage(float2 (&a)[N], std::integer_sequence<int, I...>) {
+  (dif_butterfly<N, H, I>(a), ...);
 }
 
-// In-place forward 32-point DFT (kernel e^{-2 pi i nk/32}).  Result is left in
-// bit-reversed order: X[k] == a[brev5(k)].
+// In-place forward 32-point DFT (kernel e^{-2 pi i nk/32}); X[k] == a[brev5(k)].
 DMEL_HD void radix32(float2 (&a)[32]) {
   using seq = std::make_integer_sequence<int, 16>;
-  dif_stage<16>(a, seq{});
-  dif_stage<8>(a, seq{});
-  dif_stage<4>(a, seq{});
-  dif_stage<2>(a, seq{});
-  dif_stage<1>(a, seq{});
+  dif_stage<32, 16>(a, seq{});
+  dif_stage<32, 8>(a, seq{});
+  dif_stage<32, 4>(a, seq{});
+  dif_stage<32, 2>(a, seq{});
+  dif_stage<32, 1>(a, seq{});
+}
+// In-place forward 16-point DFT; X[k] == a[brev4(k)].
+DMEL_HD void radix16(float2 (&a)[16]) {
+  using seq = std::make_integer_sequence<int, 8>;
+  dif_stage<16, 8>(a, seq{});
+  dif_stage<16, 4>(a, seq{});
+  dif_stage<16, 2>(a, seq{});
+  dif_stage<16, 1>(a, seq{});
 }
 
-// Shared-memory transpose tile of one warp: 32 rows of 32 complex, row pitch
+// Shared-memory transpose tile of one warp: rows of 32 complex, row pitch
 // 34 complex = 272 B.  272/16 is odd, so eight lanes reading 16 B each at
 // consecutive rows cover all 32 banks (LDS.128 conflict free); a row written
 // by 32 lanes as 8-byte words is contiguous (STS.64 conflict free).
-constexpr int kTilePitch = 34;                     // in float2
-constexpr int kTileFloat2 = 32 * kTilePitch;       // 1088 float2 = 8704 B
-
-// Pass 1 of the 1024-point FFT for lane n2:  v[n1] = z[32*n1 + n2] on entry.
-// Leaves  Y[n2][k1] * W_1024^{n2*k1}  at tile[k1][n2].  tw[k1] = W_1024^{n2*k1}.
-DMEL_HD void fft1024_pass1(float2 (&v)[32], const float2 (&tw)[32], float2* tile, int lane) {
-  radix32(v);
-#pragma unroll
-  for (int k1 = 0; k1 < 32; ++k1) {
-    const float2 y = v[brev5(k1)];
-    tile[k1 * kTilePitch + lane] = (k1 == 0) ? y : cmul(y, tw[k1]);
-  }
-}
-
-// Pass 2 for lane k1: reads row k1 of the tile, leaves Z[k1 + 32*k2] in
-// v[brev5(k2)].
-DMEL_HD void fft1024_pass2(float2 (&v)[32], const float2* tile, int lane) {
-  const float4* row = reinterpret_cast<const float4*>(tile + lane * kTilePitch);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const float4 t = row[j];
-    v[2 * j] = make_float2(t.x, t.y);
-    v[2 * j + 1] = make_float2(t.z, t.w);
-  }
-  radix32(v);
-}
-
-// Which register of the lane that owns bin (1024 - k) holds it, for
-// k = lane + 32*k2.  Lane 0 pairs with itself one slot later than the others.
-DMEL_HD constexpr int mirror_slot(int k2, bool sender_is_lane0) {
-  return sender_is_lane0 ? ((32 - k2) & 31) : (31 - k2);
-}
+constexpr int kTilePitch = 34;                  // in float2
+constexpr int kTile512 = 16 * kTilePitch;       // 544 float2 = 4352 B  (n_fft 1024)
+constexpr int kTile1024 = 32 * kTilePitch;      // 1088 float2 = 8704 B (n_fft 2048)
 
 DMEL_HD float fast_sqrt(float x) {
 #ifdef __CUDA_ARCH__
@@ -142,26 +127,139 @@ DMEL_HD float fast_sqrt(float x) {
 
 constexpr float kMagEps = 1e-9f;  // reference utils/spectrogram.py:76
 
-// Two real frames packed as z = a + i*b.  A = Z[k], Bm = Z[N-k].
-//   Xa[k] = (A + conj(Bm))/2 ,  Xb[k] = (A - conj(Bm))/(2i)
-// Returns sqrt(|X|^2 + 1e-9) for both frames.
-DMEL_HD void packed_pair_magnitudes(float2 A, float2 Bm, float& mag_a, float& mag_b) {
-  const float sr = A.x + Bm.x, di = A.y - Bm.y;
-  const float dr = A.x - Bm.x, si = A.y + Bm.y;
-  mag_a = fast_sqrt(fmaf(0.25f, fmaf(sr, sr, di * di), kMagEps));
-  mag_b = fast_sqrt(fmaf(0.25f, fmaf(dr, dr, si * si), kMagEps));
+// Unfold one bin pair of a real frame of 2C samples from Z = FFT_C(z):
+// with A = Z[k], Bm = Z[C-k], E = (A + conj Bm)/2, O = (A - conj Bm)/(2i),
+// w = W_{2C}^k:   X[k] = E + w*O ,  X[C-k] = conj(E - w*O).
+// Returns sqrt(|X|^2 + 1e-9) for both bins (the 1/2 is folded into the square).
+DMEL_HD void folded_magnitudes(float2 A, float2 Bm, float2 w, float& mag_k, float& mag_mirror) {
+  const float2 P = make_float2(A.x + Bm.x, A.y - Bm.y);     // 2E
+  const float2 Q = make_float2(A.y + Bm.y, Bm.x - A.x);     // 2O
+  const float2 wq = cmul(w, Q);
+  const float2 p = cadd(P, wq), m = csub(P, wq);
+  mag_k = fast_sqrt(fmaf(0.25f, fmaf(p.x, p.x, p.y * p.y), kMagEps));
+  mag_mirror = fast_sqrt(fmaf(0.25f, fmaf(m.x, m.x, m.y * m.y), kMagEps));
 }
 
-// One real frame of 2048 folded to z[n] = x[2n] + i*x[2n+1], Z = FFT_1024(z).
-// With E = (A + conj(Bm))/2, O = (A - conj(Bm))/(2i), w = W_2048^k:
-//   X[k] = E + w*O ,  X[1024-k] = conj(E - w*O)
-DMEL_HD void folded_magnitudes(float2 A, float2 Bm, float2 w, float& mag_k, float& mag_mirror) {
-  const float2 E = make_float2(0.5f * (A.x + Bm.x), 0.5f * (A.y - Bm.y));
-  const float2 O = make_float2(0.5f * (A.y + Bm.y), -0.5f * (A.x - Bm.x));
-  const float2 wo = cmul(w, O);
-  const float2 p = cadd(E, wo), m = csub(E, wo);
-  mag_k = fast_sqrt(fmaf(p.x, p.x, fmaf(p.y, p.y, kMagEps)));
-  mag_mirror = fast_sqrt(fmaf(m.x, m.x, fmaf(m.y, m.y, kMagEps)));
+// =============================================================================
+// n_fft = 1024 : 512-point complex FFT, 16 points per lane
+// =============================================================================
+// Pass 1, lane n2:  v[n1] = z[32*n1 + n2] on entry.  Leaves
+// Y[n2][k1] * W_512^{n2*k1} at tile[k1][col(n2)], where even n2 fill columns
+// 0..15 and odd n2 columns 16..31 so pass 2 reads one parity contiguously.
+// tw[k1] = W_512^{n2*k1}.
+DMEL_HD void fft512_pass1(float2 (&v)[16], const float2 (&tw)[16], float2* tile, int lane) {
+  radix16(v);
+  const int col = (lane & 1) * 16 + (lane >> 1);
+#pragma unroll
+  for (int k1 = 0; k1 < 16; ++k1) {
+    const float2 y = v[brev4(k1)];
+    tile[k1 * kTilePitch + col] = (k1 == 0) ? y : cmul(y, tw[k1]);
+  }
+}
+
+// Pass 2, lane = k1 + 16*h: radix-16 over the n2 of parity h of row k1.
+// Leaves G_h[q] = sum_m Y'[2m+h] W_16^{mq} in v[brev4(q)].
+DMEL_HD void fft512_pass2(float2 (&v)[16], const float2* tile, int lane) {
+  const float4* row = reinterpret_cast<const float4*>(tile + (lane & 15) * kTilePitch + (lane >> 4) * 16);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = row[j];
+    v[2 * j] = make_float2(t.x, t.y);
+    v[2 * j + 1] = make_float2(t.z, t.w);
+  }
+  radix16(v);
+}
+
+// Cross-lane radix-2 that finishes the 32-point DFT of a row:
+//   Z'[q + 16 r] = G_0[q] + (-1)^r W_32^q G_1[q].
+// Lane h keeps the q of parity h (q = 2j + h) and ships the other parity to its
+// partner (lane ^ 16).  combine_send picks what to ship, combine_finish consumes
+// what arrived:  zlo[j] = Z'[2j+h],  zhi[j] = Z'[2j+h+16],  i.e. bins
+// k = lane + 32*j  and  k + 256.
+DMEL_HD void combine_send(const float2 (&v)[16], int h, float2 (&send)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) send[j] = h ? v[brev4(2 * j)] : v[brev4(2 * j + 1)];
+}
+template <int J>
+DMEL_HD void combine_one(const float2 (&v)[16], const float2 (&recv)[8], int h, float2 (&zlo)[8], float2 (&zhi)[8]) {
+  const float2 a = h ? recv[J] : v[brev4(2 * J)];        // G_0[q]
+  const float2 b = h ? v[brev4(2 * J + 1)] : recv[J];    // G_1[q]
+  const float c = h ? cos32(2 * J + 1) : cos32(2 * J);   // W_32^q = c - i s
+  const float s = h ? sin32(2 * J + 1) : sin32(2 * J);
+  const float2 t = make_float2(fmaf(b.y, s, b.x * c), fmaf(-b.x, s, b.y * c));
+  zlo[J] = cadd(a, t);
+  zhi[J] = csub(a, t);
+}
+template <int... J>
+DMEL_HD void combine_all(const float2 (&v)[16], const float2 (&recv)[8], int h, float2 (&zlo)[8], float2 (&zhi)[8],
+                         std::integer_sequence<int, J...>) {
+  (combine_one<J>(v, recv, h, zlo, zhi), ...);
+}
+DMEL_HD void combine_finish(const float2 (&v)[16], const float2 (&recv)[8], int h, float2 (&zlo)[8], float2 (&zhi)[8]) {
+  combine_all(v, recv, h, zlo, zhi, std::make_integer_sequence<int, 8>{});
+}
+
+// Unfold needs Z[512-k] for k = lane + 32*j, j = 0..7.  It lives in lane
+// mirror_lane512(lane) as zhi[7-j]; lane 0 pairs with itself one slot later
+// (and with its own zlo[0] for k = 0).
+DMEL_HD int mirror_lane512(int lane) { return ((16 - (lane & 15)) + 16 * (1 - (lane >> 4))) & 31; }
+DMEL_HD void mirror_send512(const float2 (&zlo)[8], const float2 (&zhi)[8], int lane, float2 (&send)[8]) {
+  send[0] = (lane == 0) ? zlo[0] : zhi[7];
+#pragma unroll
+  for (int j = 1; j < 8; ++j) send[j] = (lane == 0) ? zhi[8 - j] : zhi[7 - j];
+}
+// W_1024^{lane + 32 j} = base * W_32^j with base = W_1024^lane
+template <int J>
+DMEL_HD void unfold_one512(const float2 (&zlo)[8], const float2 (&recv)[8], float2 base, float* mrow, int lane) {
+  float mk, mm;
+  folded_magnitudes(zlo[J], recv[J], mul_w32<J>(base), mk, mm);
+  mrow[lane + 32 * J] = mk;
+  mrow[512 - lane - 32 * J] = mm;
+}
+template <int... J>
+DMEL_HD void unfold_all512(const float2 (&zlo)[8], const float2 (&recv)[8], float2 base, float* mrow, int lane,
+                           std::integer_sequence<int, J...>) {
+  (unfold_one512<J>(zlo, recv, base, mrow, lane), ...);
+}
+// Writes the 513 magnitudes of the frame into mrow[0..512] (this lane's share).
+DMEL_HD void unfold_store512(const float2 (&zlo)[8], const float2 (&zhi)[8], const float2 (&recv)[8], float2 base,
+                             float* mrow, int lane) {
+  unfold_all512(zlo, recv, base, mrow, lane, std::make_integer_sequence<int, 8>{});
+  if (lane == 0) {  // k = 256 pairs with itself; W_1024^256 = -i
+    float mk, mm;
+    folded_magnitudes(zhi[0], zhi[0], make_float2(0.f, -1.f), mk, mm);
+    mrow[256] = mk;
+  }
+}
+
+// =============================================================================
+// n_fft = 2048 : 1024-point complex FFT, 32 points per lane
+// =============================================================================
+// Pass 1, lane n2:  v[n1] = z[32*n1 + n2].  Leaves Y[n2][k1] * W_1024^{n2*k1}
+// at tile[k1][n2].  tw[k1] = W_1024^{n2*k1}.
+DMEL_HD void fft1024_pass1(float2 (&v)[32], const float2 (&tw)[32], float2* tile, int lane) {
+  radix32(v);
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) {
+    const float2 y = v[brev5(k1)];
+    tile[k1 * kTilePitch + lane] = (k1 == 0) ? y : cmul(y, tw[k1]);
+  }
+}
+// Pass 2, lane k1: leaves Z[k1 + 32*k2] in v[brev5(k2)].
+DMEL_HD void fft1024_pass2(float2 (&v)[32], const float2* tile, int lane) {
+  const float4* row = reinterpret_cast<const float4*>(tile + lane * kTilePitch);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float4 t = row[j];
+    v[2 * j] = make_float2(t.x, t.y);
+    v[2 * j + 1] = make_float2(t.z, t.w);
+  }
+  radix32(v);
+}
+// Z[1024-k] for k = lane + 32*k2 lives in lane (32-lane)&31, register
+// brev5(mirror_slot1024(k2, that lane == 0)).
+DMEL_HD constexpr int mirror_slot1024(int k2, bool sender_is_lane0) {
+  return sender_is_lane0 ? ((32 - k2) & 31) : (31 - k2);
 }
 
 }  // namespace dmel

@@ -1,9 +1,12 @@
 // Fused waveform -> log-mel -> dMel codes kernel (sm_100a).
 //
-// One CTA owns a tile of TF consecutive frames of one utterance row:
-//   1. stage  (TF-1)*hop + n_fft  samples in shared memory, reflect-indexed at
-//      the row ends (reference utils/spectrogram.py:58-62), so the 4x frame
-//      overlap is re-read on chip, not from HBM;
+// One CTA owns tiles of TF consecutive frames of one utterance row:
+//   1. the (TF-1)*hop + n_fft samples of the NEXT tile are pulled into shared
+//      memory by one bulk async copy (cp.async.bulk + mbarrier, double
+//      buffered) while the current tile computes; row ends, where the
+//      reference reflect-pads (utils/spectrogram.py:58-62), are staged by
+//      ordinary reflect-indexed loads.  The 4x frame overlap is re-read on
+//      chip, never from HBM;
 //   2. each warp turns frames into magnitudes with the register FFT of
 //      fft_core.cuh (window multiply on load, torch.stft at :64-75, magnitude
 //      at :76) and drops them in a [frame][bin] shared tile;
@@ -25,6 +28,12 @@ constexpr float kLogClip = 1e-5f;  // reference utils/spectrogram.py:38
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 
+// what one launch writes (template parameter: dead outputs cost no instructions)
+constexpr int kOutCodes = 1;
+constexpr int kOutLogmel = 2;
+constexpr int kOutStats = 4;
+constexpr int kOutEdge = 8;  // count values within edge_eps of an interior bin edge (needs kOutCodes)
+
 struct FusedParams {
   const float* wav;         // (B, row_stride) device
   long long row_stride;     // samples between rows
@@ -37,22 +46,22 @@ struct FusedParams {
   int pad_inner;            // (n_fft - hop)/2 reflect pad of the reference
   int pad_outer;            // n_fft/2 when center=True, else 0
   int n_mels;
-  int wave_len;             // staged samples per tile
+  int wave_len;             // staged samples per tile (multiple of 4)
   int nnz;                  // banded weights
   const float* window;      // (n_fft)
-  const float2* stage_tw;   // [32][32]: W_1024^{k1*n2} at [k1*32 + n2]
-  const float2* fold_tw;    // [513]: W_2048^k (n_fft == 2048 only)
+  const float2* stage_tw;   // n_fft 1024: [16][32] W_512^{k1*n2}; n_fft 2048: [32][32] W_1024^{k1*n2}
+  const float2* fold_tw;    // [n_fft/4 + 1]: W_{n_fft}^k
   const int4* chan;         // per channel {first bin, count (mult. of 4), weight offset, 0}
   const float* weights;
   const int* lengths;       // valid samples per row, or null
-  float* logmel;            // (B, M, T) or null
-  unsigned char* codes;     // (B, M, T) or null
-  const float* q_lo;        // (M)
-  const float* q_scale;     // (M)  K / (hi - lo)
+  float* logmel;            // (B, M, T)            [kOutLogmel]
+  unsigned char* codes;     // (B, M, T)            [kOutCodes]
+  const float* q_lo;        // (M)                  [kOutCodes]
+  const float* q_scale;     // (M)  K / (hi - lo)   [kOutCodes]
   int n_bins;
-  float* run_min;           // (M) running min, updated in place, or null
+  float* run_min;           // (M) running min, updated in place [kOutStats]
   float* run_max;           // (M)
-  unsigned long long* near_edge;  // count of values within edge_eps of an interior edge, or null
+  unsigned long long* near_edge;  // [kOutEdge]
   float edge_eps;
 };
 
@@ -79,61 +88,101 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
+// ---- mbarrier + bulk async copy (TMA engine, 1-D) ----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 template <int NFFT, int TF>
 struct FusedLayout {
   static constexpr int kBins = NFFT / 2 + 1;
   static constexpr int kMagPitch = kBins;  // 513 / 1025: == 1 (mod 32), lane-per-frame reads hit 32 banks
   static constexpr int kMagFloats = TF * kMagPitch + 4;
+  static constexpr int kTileF2 = NFFT == 1024 ? kTile512 : kTile1024;
+  static constexpr int kFoldN = NFFT / 4 + 1;
   // byte offsets inside dynamic shared memory (all 16-byte aligned)
   static __host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
   static __host__ __device__ size_t tiles_off() { return 0; }
-  static __host__ __device__ size_t mags_off() { return size_t(kWarps) * kTileFloat2 * sizeof(float2); }
+  static __host__ __device__ size_t mags_off() { return size_t(kWarps) * kTileF2 * sizeof(float2); }
   static __host__ __device__ size_t wave_off() { return align16(mags_off() + size_t(kMagFloats) * 4); }
-  static __host__ __device__ size_t window_off(int wave_len) { return align16(wave_off() + size_t(wave_len) * 4); }
+  static __host__ __device__ size_t window_off(int wave_len) { return align16(wave_off() + 2 * size_t(wave_len) * 4); }
   static __host__ __device__ size_t fold_off(int wave_len) {
     return align16(window_off(wave_len) + (NFFT == 2048 ? size_t(NFFT) * 4 : 0));
   }
   static __host__ __device__ size_t chan_off(int wave_len) {
-    return align16(fold_off(wave_len) + (NFFT == 2048 ? size_t(513) * 8 : 0));
+    return align16(fold_off(wave_len) + (NFFT == 2048 ? size_t(kFoldN) * 8 : 0));
   }
   static __host__ __device__ size_t weights_off(int wave_len, int n_mels) {
     return align16(chan_off(wave_len) + size_t(n_mels) * 16);
   }
-  static __host__ __device__ size_t stats_off(int wave_len, int n_mels, int nnz) {
+  static __host__ __device__ size_t perchan_off(int wave_len, int n_mels, int nnz) {
     return align16(weights_off(wave_len, n_mels) + size_t(nnz) * 4);
   }
+  static __host__ __device__ size_t bar_off(int wave_len, int n_mels, int nnz) {
+    return align16(perchan_off(wave_len, n_mels, nnz) + size_t(n_mels) * 16);  // lo, scale, min, max
+  }
   static __host__ __device__ size_t total(int wave_len, int n_mels, int nnz) {
-    return stats_off(wave_len, n_mels, nnz) + size_t(n_mels) * 8;
+    return bar_off(wave_len, n_mels, nnz) + 16;
   }
 };
 
-template <int NFFT, int TF>
-__global__ void __launch_bounds__(kThreads, 1) dmel_fused_kernel(const FusedParams p) {
-  static_assert(NFFT == 1024 || NFFT == 2048, "register FFT core is 1024 complex points");
+template <int NFFT, int TF, int MODE>
+__global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_kernel(const FusedParams p) {
+  static_assert(NFFT == 1024 || NFFT == 2048, "register FFT cores: 512 and 1024 complex points");
   static_assert(TF == 32 || TF == 16 || TF == 8, "tile frames");
   using LY = FusedLayout<NFFT, TF>;
-  constexpr int kBins = LY::kBins;
   constexpr int kPitch = LY::kMagPitch;
+  constexpr bool kCodes = (MODE & kOutCodes) != 0, kLogmel = (MODE & kOutLogmel) != 0;
+  constexpr bool kStats = (MODE & kOutStats) != 0, kEdge = (MODE & kOutEdge) != 0;
 
   extern __shared__ __align__(16) unsigned char smem[];
   float2* tiles = reinterpret_cast<float2*>(smem + LY::tiles_off());
   float* mags = reinterpret_cast<float*>(smem + LY::mags_off());
-  float* wave = reinterpret_cast<float*>(smem + LY::wave_off());
+  float* wave0 = reinterpret_cast<float*>(smem + LY::wave_off());
   float* s_window = reinterpret_cast<float*>(smem + LY::window_off(p.wave_len));
   float2* s_fold = reinterpret_cast<float2*>(smem + LY::fold_off(p.wave_len));
   int4* s_chan = reinterpret_cast<int4*>(smem + LY::chan_off(p.wave_len));
   float* s_weights = reinterpret_cast<float*>(smem + LY::weights_off(p.wave_len, p.n_mels));
-  float* s_min = reinterpret_cast<float*>(smem + LY::stats_off(p.wave_len, p.n_mels, p.nnz));
+  float* s_lo = reinterpret_cast<float*>(smem + LY::perchan_off(p.wave_len, p.n_mels, p.nnz));
+  float* s_scale = s_lo + p.n_mels;
+  float* s_min = s_scale + p.n_mels;
   float* s_max = s_min + p.n_mels;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LY::bar_off(p.wave_len, p.n_mels, p.nnz));
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  float2* my_tile = tiles + warp * kTileFloat2;
+  float2* my_tile = tiles + warp * LY::kTileF2;
 
   // ---- per-CTA constants -------------------------------------------------
   for (int i = tid; i < p.n_mels; i += kThreads) {
     s_chan[i] = p.chan[i];
+    if constexpr (kCodes) {
+      s_lo[i] = p.q_lo[i];
+      s_scale[i] = p.q_scale[i];
+    }
     s_min[i] = __int_as_float(0x7f800000);
     s_max[i] = __int_as_float(0xff800000);
   }
@@ -141,92 +190,139 @@ __global__ void __launch_bounds__(kThreads, 1) dmel_fused_kernel(const FusedPara
   if (tid < 4) mags[TF * kPitch + tid] = 0.f;  // banded spans may over-read 3 floats
   if constexpr (NFFT == 2048) {
     for (int i = tid; i < NFFT; i += kThreads) s_window[i] = p.window[i];
-    for (int i = tid; i < 513; i += kThreads) s_fold[i] = p.fold_tw[i];
+    for (int i = tid; i < LY::kFoldN; i += kThreads) s_fold[i] = p.fold_tw[i];
+  }
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
   }
 
-  // per-lane inter-pass twiddles W_1024^{lane*k1}; window taps for the packed path
-  float2 tw[32];
+  // per-lane constants kept in registers for the whole kernel
+  constexpr int kPts = NFFT == 1024 ? 16 : 32;  // complex points per lane
+  float2 tw[kPts];                              // inter-pass twiddles W_{NFFT/2}^{lane*k1}
 #pragma unroll
-  for (int k1 = 0; k1 < 32; ++k1) tw[k1] = p.stage_tw[k1 * 32 + lane];
-  float win[NFFT == 1024 ? 32 : 1];
+  for (int k1 = 0; k1 < kPts; ++k1) tw[k1] = p.stage_tw[k1 * 32 + lane];
+  float2 win[NFFT == 1024 ? 16 : 1];            // window taps of this lane's samples
+  float2 fold_base = make_float2(1.f, 0.f);     // W_1024^lane
   if constexpr (NFFT == 1024) {
 #pragma unroll
-    for (int n1 = 0; n1 < 32; ++n1) win[n1] = p.window[32 * n1 + lane];
+    for (int n1 = 0; n1 < 16; ++n1) {
+      const int idx = 2 * (32 * n1 + lane);
+      win[n1] = make_float2(p.window[idx], p.window[idx + 1]);
+    }
+    fold_base = p.fold_tw[lane];
   }
 
   const int padded_len = p.n_samples + 2 * p.pad_inner + 2 * p.pad_outer;
+  const bool hop_even = (p.hop & 1) == 0;
+  const bool row_vec_ok = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0) && ((p.row_stride & 3) == 0);
   unsigned long long edge_hits = 0;
+  uint32_t phase_bits = 0;  // bit b: parity to wait for on bars[b]
 
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-    const int row = tile / p.tiles_per_row;
-    const int t0 = (tile - row * p.tiles_per_row) * TF;
-    const float* src = p.wav + (long long)row * p.row_stride;
-    int n_valid = p.n_frames;
+  // Tile geometry helpers (everything CTA-uniform).
+  auto tile_row = [&](int tile) { return tile / p.tiles_per_row; };
+  auto tile_t0 = [&](int tile) { return (tile - tile_row(tile) * p.tiles_per_row) * TF; };
+  auto row_valid = [&](int row) {
+    int nv = p.n_frames;
     if (p.lengths) {
-      n_valid = p.lengths[row] / p.hop;
-      n_valid = n_valid < p.n_frames ? n_valid : p.n_frames;
+      nv = p.lengths[row] / p.hop;
+      nv = nv < p.n_frames ? nv : p.n_frames;
     }
-    const bool need_values = p.logmel != nullptr;  // log-mel output covers every frame
-    const bool tile_dead = !need_values && t0 >= n_valid;
-
-    __syncthreads();  // previous tile: mel phase done with mags, FFT done with wave
-
-    if (!tile_dead) {
-      // ---- 1. stage the waveform tile -----------------------------------
-      const int j0 = t0 * p.hop;                      // first padded-row position
-      const int s0 = j0 - p.pad_inner - p.pad_outer;  // its source sample, if interior
-      const bool interior = s0 >= 0 && s0 + p.wave_len <= p.n_samples &&
-                            ((reinterpret_cast<uintptr_t>(src + s0) & 15) == 0) && (p.wave_len % 4 == 0);
-      if (interior) {
-        const float4* g4 = reinterpret_cast<const float4*>(src + s0);
-        float4* w4 = reinterpret_cast<float4*>(wave);
-        for (int i = tid; i < p.wave_len / 4; i += kThreads) w4[i] = __ldg(g4 + i);
-      } else {
-        for (int i = tid; i < p.wave_len; i += kThreads) {
-          const int j = j0 + i;
-          float x = 0.f;
-          if (j < padded_len) x = __ldg(src + reflect_src(j, p.n_samples, p.pad_inner, p.pad_outer));
-          wave[i] = x;
-        }
+    return nv;
+  };
+  // log-mel output needs every frame; otherwise tiles past the valid length are skipped
+  auto tile_dead = [&](int tile) { return !kLogmel && tile_t0(tile) >= row_valid(tile_row(tile)); };
+  auto tile_async = [&](int tile) {
+    const int s0 = tile_t0(tile) * p.hop - p.pad_inner - p.pad_outer;
+    return row_vec_ok && s0 >= 0 && (s0 & 3) == 0 && s0 + p.wave_len <= p.n_samples;
+  };
+  // Start filling wave buffer b with the samples of `tile`.
+  auto stage = [&](int tile, int b) {
+    if (tile_dead(tile)) return;
+    float* wave = wave0 + b * p.wave_len;
+    const float* src = p.wav + (long long)tile_row(tile) * p.row_stride;
+    const int j0 = tile_t0(tile) * p.hop;  // first position in the padded row
+    if (tile_async(tile)) {
+      if (tid == 0) {
+        fence_proxy_async();  // earlier generic-proxy reads of this buffer are ordered before the async write
+        mbar_expect_tx(&bars[b], p.wave_len * 4);
+        bulk_copy_g2s(wave, src + (j0 - p.pad_inner - p.pad_outer), p.wave_len * 4, &bars[b]);
       }
-      __syncthreads();
+    } else {
+      for (int i = tid; i < p.wave_len; i += kThreads) {
+        const int j = j0 + i;
+        float x = 0.f;
+        if (j < padded_len) x = __ldg(src + reflect_src(j, p.n_samples, p.pad_inner, p.pad_outer));
+        wave[i] = x;
+      }
+    }
+  };
 
-      // ---- 2. FFT -> magnitudes -----------------------------------------
+  __syncthreads();  // constants + barrier init visible
+  int tile = blockIdx.x;
+  if (tile < p.n_tiles) stage(tile, 0);
+
+  for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    const int b = it & 1;
+    const int row = tile_row(tile);
+    const int t0 = tile_t0(tile);
+    const int n_valid = row_valid(row);
+    const bool dead = tile_dead(tile);
+    const float* wave = wave0 + b * p.wave_len;
+
+    // ---- 1. this tile's samples are in wave[b]; start fetching the next tile
+    if (!dead) {
+      if (tile_async(tile)) {
+        mbar_wait(&bars[b], (phase_bits >> b) & 1u);
+        phase_bits ^= 1u << b;
+      } else {
+        __syncthreads();  // plain stores of all threads
+      }
+    }
+    if (tile + (int)gridDim.x < p.n_tiles) stage(tile + gridDim.x, b ^ 1);
+
+    // ---- 2. FFT -> magnitudes ------------------------------------------------
+    if (!dead) {
       if constexpr (NFFT == 1024) {
-        for (int pr = warp; pr < TF / 2; pr += kWarps) {
-          const float* fa = wave + (2 * pr) * p.hop;
-          const float* fb = fa + p.hop;
-          float2 v[32];
+        const int h = lane >> 4;
+        const int partner = mirror_lane512(lane);
+#pragma unroll 1
+        for (int fr = warp; fr < TF; fr += kWarps) {
+          const float* fa = wave + fr * p.hop;
+          float2 v[16];
+          if (hop_even) {
+            const float2* f2 = reinterpret_cast<const float2*>(fa);
 #pragma unroll
-          for (int n1 = 0; n1 < 32; ++n1) {
-            const int idx = 32 * n1 + lane;
-            v[n1] = make_float2(fa[idx] * win[n1], fb[idx] * win[n1]);
-          }
-          __syncwarp();
-          fft1024_pass1(v, tw, my_tile, lane);
-          __syncwarp();
-          fft1024_pass2(v, my_tile, lane);
-          float* ma = mags + (2 * pr) * kPitch;
-          float* mb = ma + kPitch;
-          const int partner = (32 - lane) & 31;
+            for (int n1 = 0; n1 < 16; ++n1) {
+              const float2 x = f2[32 * n1 + lane];
+              v[n1] = make_float2(x.x * win[n1].x, x.y * win[n1].y);
+            }
+          } else {
 #pragma unroll
-          for (int k2 = 0; k2 < 16; ++k2) {
-            const float2 send = (lane == 0) ? v[brev5(mirror_slot(k2, true))] : v[brev5(mirror_slot(k2, false))];
-            const float2 bm = make_float2(__shfl_sync(0xffffffffu, send.x, partner),
-                                          __shfl_sync(0xffffffffu, send.y, partner));
-            float xa, xb;
-            packed_pair_magnitudes(v[brev5(k2)], bm, xa, xb);
-            ma[32 * k2 + lane] = xa;
-            mb[32 * k2 + lane] = xb;
+            for (int n1 = 0; n1 < 16; ++n1) {
+              const int idx = 2 * (32 * n1 + lane);
+              v[n1] = make_float2(fa[idx] * win[n1].x, fa[idx + 1] * win[n1].y);
+            }
           }
-          if (lane == 0) {  // Nyquist bin 512 pairs with itself
-            float xa, xb;
-            packed_pair_magnitudes(v[brev5(16)], v[brev5(16)], xa, xb);
-            ma[512] = xa;
-            mb[512] = xb;
-          }
+          __syncwarp();  // previous frame's pass-2 reads of my_tile are done
+          fft512_pass1(v, tw, my_tile, lane);
+          __syncwarp();
+          fft512_pass2(v, my_tile, lane);
+          float2 send[8], recv[8], zlo[8], zhi[8];
+          combine_send(v, h, send);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            recv[j] = make_float2(__shfl_xor_sync(0xffffffffu, send[j].x, 16), __shfl_xor_sync(0xffffffffu, send[j].y, 16));
+          combine_finish(v, recv, h, zlo, zhi);
+          mirror_send512(zlo, zhi, lane, send);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            recv[j] = make_float2(__shfl_sync(0xffffffffu, send[j].x, partner), __shfl_sync(0xffffffffu, send[j].y, partner));
+          unfold_store512(zlo, zhi, recv, fold_base, mags + fr * kPitch, lane);
         }
       } else {
+#pragma unroll 1
         for (int fr = warp; fr < TF; fr += kWarps) {
           const float* fa = wave + fr * p.hop;
           float2 v[32];
@@ -244,7 +340,8 @@ __global__ void __launch_bounds__(kThreads, 1) dmel_fused_kernel(const FusedPara
           const int partner = (32 - lane) & 31;
 #pragma unroll
           for (int k2 = 0; k2 < 16; ++k2) {
-            const float2 send = (lane == 0) ? v[brev5(mirror_slot(k2, true))] : v[brev5(mirror_slot(k2, false))];
+            const float2 send =
+                (lane == 0) ? v[brev5(mirror_slot1024(k2, true))] : v[brev5(mirror_slot1024(k2, false))];
             const float2 bm = make_float2(__shfl_sync(0xffffffffu, send.x, partner),
                                           __shfl_sync(0xffffffffu, send.y, partner));
             const int k = 32 * k2 + lane;
@@ -264,66 +361,72 @@ __global__ void __launch_bounds__(kThreads, 1) dmel_fused_kernel(const FusedPara
     __syncthreads();
 
     // ---- 3. mel filterbank, log, quantise --------------------------------
-    constexpr int kGroups = 32 / TF;  // channels handled side by side in one warp
-    const int fr = lane % TF;
-    const int sub = lane / TF;
-    const int t = t0 + fr;
-    const float* mrow = mags + fr * kPitch;
-    // the channel loop is warp-uniform (shuffles inside); a group past the last channel idles
-    for (int mb = warp * kGroups; mb < p.n_mels; mb += kWarps * kGroups) {
-      const int m = mb + sub;
-      const bool live = m < p.n_mels;
-      float value = 0.f;
-      if (live && !tile_dead) {
-        const int4 c = s_chan[m];
-        const float4* w4 = reinterpret_cast<const float4*>(s_weights + c.z);
-        const float* x = mrow + c.x;
-        float acc = 0.f;
-        for (int i = 0; i < c.y; i += 4) {
-          const float4 w = w4[i >> 2];
-          acc = fmaf(w.x, x[i], acc);
-          acc = fmaf(w.y, x[i + 1], acc);
-          acc = fmaf(w.z, x[i + 2], acc);
-          acc = fmaf(w.w, x[i + 3], acc);
+    {
+      constexpr int kGroups = 32 / TF;  // channels handled side by side in one warp
+      const int fr = lane % TF;
+      const int sub = lane / TF;
+      const int t = t0 + fr;
+      const bool in_row = t < p.n_frames;
+      const bool valid = t < n_valid;
+      const float* mrow = mags + fr * kPitch;
+      const size_t out0 = (size_t)row * p.n_mels * p.n_frames + t;
+      const float kmax = float(p.n_bins - 1);
+      // the channel loop is warp-uniform (shuffles inside); a group past the last channel idles
+#pragma unroll 1
+      for (int mb = warp * kGroups; mb < p.n_mels; mb += kWarps * kGroups) {
+        const int m = mb + sub;
+        const bool live = m < p.n_mels;
+        float value = 0.f;
+        if (live && !dead) {
+          const int4 c = s_chan[m];
+          const float4* w4 = reinterpret_cast<const float4*>(s_weights + c.z);
+          const float* x = mrow + c.x;
+          float acc = 0.f;
+          for (int i = 0; i < c.y; i += 4) {
+            const float4 w = w4[i >> 2];
+            acc = fmaf(w.x, x[i], acc);
+            acc = fmaf(w.y, x[i + 1], acc);
+            acc = fmaf(w.z, x[i + 2], acc);
+            acc = fmaf(w.w, x[i + 3], acc);
+          }
+          value = __logf(fmaxf(acc, kLogClip));
         }
-        value = __logf(fmaxf(acc, kLogClip));
-      }
-      const bool in_row = live && t < p.n_frames;
-      const bool valid = live && t < n_valid;
-      const long long o = ((long long)row * p.n_mels + m) * p.n_frames + t;
-      if (p.logmel && in_row) p.logmel[o] = value;
-      if (p.codes && in_row) {
-        unsigned char code = 0;
-        if (valid) {
-          const float pos = __fmul_rn(__fsub_rn(value, __ldg(p.q_lo + m)), __ldg(p.q_scale + m));
-          const float q = fminf(fmaxf(floorf(pos), 0.f), float(p.n_bins - 1));
-          code = (unsigned char)q;
-          if (p.near_edge) {
-            const float e = fminf(fmaxf(rintf(pos), 1.f), float(p.n_bins - 1));
-            if (fabsf(pos - e) < p.edge_eps * __ldg(p.q_scale + m)) ++edge_hits;
+        const size_t o = out0 + (size_t)m * p.n_frames;
+        if constexpr (kLogmel) {
+          if (live && in_row) p.logmel[o] = value;
+        }
+        if constexpr (kCodes) {
+          if (live && in_row) {
+            const float sc = s_scale[m];
+            const float pos = __fmul_rn(__fsub_rn(value, s_lo[m]), sc);
+            const float q = fminf(fmaxf(floorf(pos), 0.f), kmax);
+            p.codes[o] = valid ? (unsigned char)q : (unsigned char)0;
+            if constexpr (kEdge) {
+              const float e = fminf(fmaxf(rintf(pos), 1.f), kmax);
+              if (valid && fabsf(pos - e) < p.edge_eps * sc) ++edge_hits;
+            }
           }
         }
-        p.codes[o] = code;
-      }
-      if (p.run_min) {
-        float lo = valid ? value : __int_as_float(0x7f800000);
-        float hi = valid ? value : __int_as_float(0xff800000);
+        if constexpr (kStats) {
+          float lo = (valid && live) ? value : __int_as_float(0x7f800000);
+          float hi = (valid && live) ? value : __int_as_float(0xff800000);
 #pragma unroll
-        for (int d = TF / 2; d >= 1; d >>= 1) {
-          lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-          hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
-        }
-        if (fr == 0 && live) {  // channel m always belongs to this lane of this warp: no race
-          s_min[m] = fminf(s_min[m], lo);
-          s_max[m] = fmaxf(s_max[m], hi);
+          for (int d = TF / 2; d >= 1; d >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+          }
+          if (fr == 0 && live) {  // channel m always belongs to this lane of this warp: no race
+            s_min[m] = fminf(s_min[m], lo);
+            s_max[m] = fmaxf(s_max[m], hi);
+          }
         }
       }
     }
+    __syncthreads();  // mags and wave[b] are free again
   }
 
   // ---- flush per-CTA statistics -------------------------------------------
-  if (p.run_min) {
-    __syncthreads();
+  if constexpr (kStats) {
     for (int m = tid; m < p.n_mels; m += kThreads) {
       const float lo = s_min[m], hi = s_max[m];
       if (lo <= hi) {
@@ -332,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 1) dmel_fused_kernel(const FusedPara
       }
     }
   }
-  if (p.near_edge) {
+  if constexpr (kEdge) {
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) edge_hits += __shfl_xor_sync(0xffffffffu, edge_hits, d);
     if (lane == 0 && edge_hits) atomicAdd(p.near_edge, edge_hits);
