@@ -58,6 +58,7 @@ struct dmel_plan {
   int ctas_per_sm = 1;
   int wave_len = 0;
   int nnz = 0;
+  int n_chan_pad = 0;  // n_mels rounded up to the channel-group size 32 / tile_frames
   size_t smem_bytes = 0;
   float* d_window = nullptr;
   float2* d_stage_tw = nullptr;
@@ -123,6 +124,43 @@ cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int gr
   }
 }
 
+// Banded form of the (n_mels, n_freq) filterbank the kernel reads: per channel the contiguous
+// non-zero span, starting on a multiple of 4 bins (the kernel fetches magnitudes with 16-byte
+// loads).  `group` adjacent channels are evaluated side by side in one warp, so their spans are
+// zero-padded to one common length (a multiple of 4, at least 4) and phantom channels complete
+// the last group; the bin loop is then uniform across the warp.
+void band_filterbank(const float* basis, int n_mels, int n_freq, int group, std::vector<int4>* chan,
+                     std::vector<float>* weights) {
+  const int n_pad = (n_mels + group - 1) / group * group;
+  chan->assign(n_pad, make_int4(0, 4, 0, 0));
+  weights->clear();
+  std::vector<int> first(n_pad, 0), last(n_pad, -1);
+  for (int m = 0; m < n_mels; ++m) {
+    const float* row = basis + (size_t)m * n_freq;
+    int f0 = -1, f1 = -1;
+    for (int f = 0; f < n_freq; ++f)
+      if (row[f] != 0.f) {
+        if (f0 < 0) f0 = f;
+        f1 = f;
+      }
+    first[m] = f0 < 0 ? 0 : (f0 & ~3);
+    last[m] = f1;
+  }
+  for (int g = 0; g < n_pad; g += group) {
+    int count = 4;
+    for (int m = g; m < g + group; ++m) count = std::max(count, (last[m] - first[m] + 1 + 3) / 4 * 4);
+    const int pitch = n_freq + 3;  // FusedLayout::kMagPitch, a multiple of 4
+    for (int m = g; m < g + group; ++m) {
+      first[m] = std::min(first[m], pitch - count);  // keep the padded span inside the frame's row
+      (*chan)[m] = make_int4(first[m], count, (int)weights->size(), 0);
+      for (int i = 0; i < count; ++i) {
+        const int f = first[m] + i;
+        weights->push_back((m < n_mels && f >= 0 && f <= last[m]) ? basis[(size_t)m * n_freq + f] : 0.f);
+      }
+    }
+  }
+}
+
 long long num_frames(const dmel_plan* plan, long long n_samples) {
   const long long padded = n_samples + 2LL * plan->pad_inner + 2LL * plan->pad_outer;
   if (padded < plan->n_fft) return 0;
@@ -160,6 +198,7 @@ int prepare_fused(dmel_plan* plan, const float* wav, long long n_rows, long long
   p->pad_inner = plan->pad_inner;
   p->pad_outer = plan->pad_outer;
   p->n_mels = plan->n_mels;
+  p->n_chan_pad = plan->n_chan_pad;
   p->wave_len = plan->wave_len;
   p->nnz = plan->nnz;
   p->window = plan->d_window;
@@ -233,29 +272,11 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
   plan->pad_inner = (n_fft - hop_length) / 2;  // reference utils/spectrogram.py:58
   plan->pad_outer = center ? n_fft / 2 : 0;
 
-  // banded filterbank: per channel the contiguous non-zero span, padded to x4
-  const int n_freq = n_fft / 2 + 1;
-  std::vector<int4> chan(n_mels);
-  std::vector<float> weights;
-  for (int m = 0; m < n_mels; ++m) {
-    const float* row = mel_basis_host + (size_t)m * n_freq;
-    int first = -1, last = -1;
-    for (int f = 0; f < n_freq; ++f) {
-      if (!std::isfinite(row[f])) {
-        delete plan;
-        return fail(DMEL_ERR_INVALID, "mel_basis[%d][%d] is not finite", m, f);
-      }
-      if (row[f] != 0.f) {
-        if (first < 0) first = f;
-        last = f;
-      }
+  for (size_t i = 0; i < (size_t)n_mels * (n_fft / 2 + 1); ++i)
+    if (!std::isfinite(mel_basis_host[i])) {
+      delete plan;
+      return fail(DMEL_ERR_INVALID, "mel_basis[%zu] is not finite", i);
     }
-    const int count = first < 0 ? 0 : last - first + 1;
-    const int count4 = (count + 3) / 4 * 4;
-    chan[m] = make_int4(first < 0 ? 0 : first, count4, (int)weights.size(), 0);
-    for (int i = 0; i < count4; ++i) weights.push_back(i < count ? row[first + i] : 0.f);
-  }
-  plan->nnz = (int)weights.size();
 
   // frame tile: prefer one that lets two CTAs share an SM (n_fft 1024 kernels are built for
   // 128 registers / 2 CTAs), else the largest that fits at all
@@ -263,16 +284,21 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
   DMEL_CUDA(cudaDeviceGetAttribute(&max_sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, plan->device));
   const size_t half_sm = (size_t)max_sm_smem / 2 - 1024;  // 1 KB per CTA is reserved by the driver
   const int candidates[2] = {16, 8};
+  std::vector<int4> chan;
+  std::vector<float> weights;
   for (int pass = 0; pass < 2 && !plan->tile_frames; ++pass)
     for (int tf : candidates) {
+      band_filterbank(mel_basis_host, n_mels, n_fft / 2 + 1, 32 / tf, &chan, &weights);
       const int wave_len = ((tf - 1) * hop_length + n_fft + 3) / 4 * 4;
-      const size_t need = fused_smem_for(n_fft, tf, wave_len, n_mels, plan->nnz);
+      const size_t need = fused_smem_for(n_fft, tf, wave_len, (int)chan.size(), (int)weights.size());
       const size_t limit = (pass == 0 && n_fft == 1024) ? half_sm : (size_t)plan->max_smem;
       if (need <= limit) {
         plan->tile_frames = tf;
         plan->wave_len = wave_len;
         plan->smem_bytes = need;
         plan->ctas_per_sm = (n_fft == 1024 && need <= half_sm) ? 2 : 1;
+        plan->nnz = (int)weights.size();
+        plan->n_chan_pad = (int)chan.size();
         break;
       }
     }

@@ -115,6 +115,17 @@ constexpr int kTilePitch = 34;                  // in float2
 constexpr int kTile512 = 16 * kTilePitch;       // 544 float2 = 4352 B  (n_fft 1024)
 constexpr int kTile1024 = 32 * kTilePitch;      // 1088 float2 = 8704 B (n_fft 2048)
 
+// natural log via MUFU.LG2 (inputs here are clamped to >= 1e-5, so no denormal handling)
+DMEL_HD float fast_log(float x) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 0.69314718055994531f;
+#else
+  return logf(x);
+#endif
+}
+
 DMEL_HD float fast_sqrt(float x) {
 #ifdef __CUDA_ARCH__
   float r;
@@ -146,10 +157,15 @@ DMEL_HD void folded_magnitudes(float2 A, float2 Bm, float2 w, float& mag_k, floa
 // Pass 1, lane n2:  v[n1] = z[32*n1 + n2] on entry.  Leaves
 // Y[n2][k1] * W_512^{n2*k1} at tile[k1][col(n2)], where even n2 fill columns
 // 0..15 and odd n2 columns 16..31 so pass 2 reads one parity contiguously.
-// tw[k1] = W_512^{n2*k1}.
+// The odd block is rotated by 8 columns: a 64-bit shared store is served per
+// half-warp, and without the rotation the 8 even and 8 odd lanes of a half-warp
+// would land on the same 16 banks.  Pass 2 therefore sees the odd-parity inputs
+// circularly shifted by 8, i.e. its outputs are (-1)^q G_1[q]; combine_one folds
+// that sign into its constants.  tw[k1] = W_512^{n2*k1}.
 DMEL_HD void fft512_pass1(float2 (&v)[16], const float2 (&tw)[16], float2* tile, int lane) {
   radix16(v);
-  const int col = (lane & 1) * 16 + (lane >> 1);
+  const int odd = lane & 1;
+  const int col = odd * 16 + (((lane >> 1) + 8 * odd) & 15);
 #pragma unroll
   for (int k1 = 0; k1 < 16; ++k1) {
     const float2 y = v[brev4(k1)];
@@ -158,7 +174,8 @@ DMEL_HD void fft512_pass1(float2 (&v)[16], const float2 (&tw)[16], float2* tile,
 }
 
 // Pass 2, lane = k1 + 16*h: radix-16 over the n2 of parity h of row k1.
-// Leaves G_h[q] = sum_m Y'[2m+h] W_16^{mq} in v[brev4(q)].
+// Leaves G_0[q] (h = 0) or (-1)^q G_1[q] (h = 1) in v[brev4(q)], where
+// G_h[q] = sum_m Y'[2m+h] W_16^{mq}.
 DMEL_HD void fft512_pass2(float2 (&v)[16], const float2* tile, int lane) {
   const float4* row = reinterpret_cast<const float4*>(tile + (lane & 15) * kTilePitch + (lane >> 4) * 16);
 #pragma unroll
@@ -183,9 +200,9 @@ DMEL_HD void combine_send(const float2 (&v)[16], int h, float2 (&send)[8]) {
 template <int J>
 DMEL_HD void combine_one(const float2 (&v)[16], const float2 (&recv)[8], int h, float2 (&zlo)[8], float2 (&zhi)[8]) {
   const float2 a = h ? recv[J] : v[brev4(2 * J)];        // G_0[q]
-  const float2 b = h ? v[brev4(2 * J + 1)] : recv[J];    // G_1[q]
-  const float c = h ? cos32(2 * J + 1) : cos32(2 * J);   // W_32^q = c - i s
-  const float s = h ? sin32(2 * J + 1) : sin32(2 * J);
+  const float2 b = h ? v[brev4(2 * J + 1)] : recv[J];    // G_1[q] for h = 0 (q even), -G_1[q] for h = 1 (q odd)
+  const float c = h ? -cos32(2 * J + 1) : cos32(2 * J);  // W_32^q = c - i s, sign of the rotated read folded in
+  const float s = h ? -sin32(2 * J + 1) : sin32(2 * J);
   const float2 t = make_float2(fmaf(b.y, s, b.x * c), fmaf(-b.x, s, b.y * c));
   zlo[J] = cadd(a, t);
   zhi[J] = csub(a, t);

@@ -46,12 +46,13 @@ struct FusedParams {
   int pad_inner;            // (n_fft - hop)/2 reflect pad of the reference
   int pad_outer;            // n_fft/2 when center=True, else 0
   int n_mels;
+  int n_chan_pad;           // n_mels rounded up to the channel-group size 32/TF
   int wave_len;             // staged samples per tile (multiple of 4)
   int nnz;                  // banded weights
   const float* window;      // (n_fft)
   const float2* stage_tw;   // n_fft 1024: [16][32] W_512^{k1*n2}; n_fft 2048: [32][32] W_1024^{k1*n2}
   const float2* fold_tw;    // [n_fft/4 + 1]: W_{n_fft}^k
-  const int4* chan;         // per channel {first bin, count (mult. of 4), weight offset, 0}
+  const int4* chan;         // (n_chan_pad) {first bin (mult. of 4), count (mult. of 4, same within a group), weight offset, 0}
   const float* weights;
   const int* lengths;       // valid samples per row, or null
   float* logmel;            // (B, M, T)            [kOutLogmel]
@@ -118,8 +119,11 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
 template <int NFFT, int TF>
 struct FusedLayout {
   static constexpr int kBins = NFFT / 2 + 1;
-  static constexpr int kMagPitch = kBins;  // 513 / 1025: == 1 (mod 32), lane-per-frame reads hit 32 banks
-  static constexpr int kMagFloats = TF * kMagPitch + 4;
+  // row pitch 516 / 1028 floats: a multiple of 4 so a lane can fetch four bins of its frame with
+  // one LDS.128, and == 4 (mod 32) so the eight lanes of a quarter-warp (eight frames) cover all
+  // 32 banks.  64 floats of zeroed tail: a group's common span length may run past its last row.
+  static constexpr int kMagPitch = kBins + 3;
+  static constexpr int kMagFloats = TF * kMagPitch + 64;
   static constexpr int kTileF2 = NFFT == 1024 ? kTile512 : kTile1024;
   static constexpr int kFoldN = NFFT / 4 + 1;
   // byte offsets inside dynamic shared memory (all 16-byte aligned)
@@ -134,18 +138,27 @@ struct FusedLayout {
   static __host__ __device__ size_t chan_off(int wave_len) {
     return align16(fold_off(wave_len) + (NFFT == 2048 ? size_t(kFoldN) * 8 : 0));
   }
-  static __host__ __device__ size_t weights_off(int wave_len, int n_mels) {
-    return align16(chan_off(wave_len) + size_t(n_mels) * 16);
+  // n_chan = channel count padded to the group size
+  static __host__ __device__ size_t weights_off(int wave_len, int n_chan) {
+    return align16(chan_off(wave_len) + size_t(n_chan) * 16);
   }
-  static __host__ __device__ size_t perchan_off(int wave_len, int n_mels, int nnz) {
-    return align16(weights_off(wave_len, n_mels) + size_t(nnz) * 4);
+  static __host__ __device__ size_t perchan_off(int wave_len, int n_chan, int nnz) {
+    return align16(weights_off(wave_len, n_chan) + size_t(nnz) * 4);
   }
-  static __host__ __device__ size_t bar_off(int wave_len, int n_mels, int nnz) {
-    return align16(perchan_off(wave_len, n_mels, nnz) + size_t(n_mels) * 16);  // lo, scale, min, max
+  static __host__ __device__ size_t bar_off(int wave_len, int n_chan, int nnz) {
+    return align16(perchan_off(wave_len, n_chan, nnz) + size_t(n_chan) * 16);  // lo, scale, min, max
   }
-  static __host__ __device__ size_t total(int wave_len, int n_mels, int nnz) {
-    return bar_off(wave_len, n_mels, nnz) + 16;
+  static __host__ __device__ size_t total(int wave_len, int n_chan, int nnz) {
+    return bar_off(wave_len, n_chan, nnz) + 16;
   }
+};
+
+// Everything the tile loop needs to know about one tile; CTA-uniform.
+struct TileInfo {
+  int row, t0, n_valid;
+  int frame_limit;  // frames of this tile worth computing (t0-relative), 0 = skip the tile
+  bool async;       // staged by the bulk-copy engine (interior, 16-byte aligned) or by plain loads
+  long long src0;   // sample offset of padded-row position t0*hop in the flat waveform, if interior
 };
 
 template <int NFFT, int TF, int MODE>
@@ -164,12 +177,12 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
   float* s_window = reinterpret_cast<float*>(smem + LY::window_off(p.wave_len));
   float2* s_fold = reinterpret_cast<float2*>(smem + LY::fold_off(p.wave_len));
   int4* s_chan = reinterpret_cast<int4*>(smem + LY::chan_off(p.wave_len));
-  float* s_weights = reinterpret_cast<float*>(smem + LY::weights_off(p.wave_len, p.n_mels));
-  float* s_lo = reinterpret_cast<float*>(smem + LY::perchan_off(p.wave_len, p.n_mels, p.nnz));
-  float* s_scale = s_lo + p.n_mels;
-  float* s_min = s_scale + p.n_mels;
-  float* s_max = s_min + p.n_mels;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LY::bar_off(p.wave_len, p.n_mels, p.nnz));
+  float* s_weights = reinterpret_cast<float*>(smem + LY::weights_off(p.wave_len, p.n_chan_pad));
+  float* s_lo = reinterpret_cast<float*>(smem + LY::perchan_off(p.wave_len, p.n_chan_pad, p.nnz));
+  float* s_scale = s_lo + p.n_chan_pad;
+  float* s_min = s_scale + p.n_chan_pad;
+  float* s_max = s_min + p.n_chan_pad;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LY::bar_off(p.wave_len, p.n_chan_pad, p.nnz));
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -177,17 +190,16 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
   float2* my_tile = tiles + warp * LY::kTileF2;
 
   // ---- per-CTA constants -------------------------------------------------
-  for (int i = tid; i < p.n_mels; i += kThreads) {
+  for (int i = tid; i < p.n_chan_pad; i += kThreads) {
     s_chan[i] = p.chan[i];
-    if constexpr (kCodes) {
-      s_lo[i] = p.q_lo[i];
-      s_scale[i] = p.q_scale[i];
-    }
+    const bool real = i < p.n_mels;
+    s_lo[i] = (kCodes && real) ? p.q_lo[i] : 0.f;
+    s_scale[i] = (kCodes && real) ? p.q_scale[i] : 0.f;
     s_min[i] = __int_as_float(0x7f800000);
     s_max[i] = __int_as_float(0xff800000);
   }
   for (int i = tid; i < p.nnz; i += kThreads) s_weights[i] = p.weights[i];
-  if (tid < 4) mags[TF * kPitch + tid] = 0.f;  // banded spans may over-read 3 floats
+  for (int i = tid; i < LY::kMagFloats; i += kThreads) mags[i] = 0.f;  // pad columns and tail stay zero
   if constexpr (NFFT == 2048) {
     for (int i = tid; i < NFFT; i += kThreads) s_window[i] = p.window[i];
     for (int i = tid; i < LY::kFoldN; i += kThreads) s_fold[i] = p.fold_tw[i];
@@ -220,36 +232,36 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
   unsigned long long edge_hits = 0;
   uint32_t phase_bits = 0;  // bit b: parity to wait for on bars[b]
 
-  // Tile geometry helpers (everything CTA-uniform).
-  auto tile_row = [&](int tile) { return tile / p.tiles_per_row; };
-  auto tile_t0 = [&](int tile) { return (tile - tile_row(tile) * p.tiles_per_row) * TF; };
-  auto row_valid = [&](int row) {
-    int nv = p.n_frames;
+  auto describe = [&](int tile) {
+    TileInfo ti;
+    ti.row = tile / p.tiles_per_row;
+    ti.t0 = (tile - ti.row * p.tiles_per_row) * TF;
+    ti.n_valid = p.n_frames;
     if (p.lengths) {
-      nv = p.lengths[row] / p.hop;
-      nv = nv < p.n_frames ? nv : p.n_frames;
+      const int nv = p.lengths[ti.row] / p.hop;
+      ti.n_valid = nv < p.n_frames ? nv : p.n_frames;
     }
-    return nv;
+    // log-mel output covers every frame of the row; codes / statistics only the valid ones
+    const int last = (kLogmel ? p.n_frames : ti.n_valid) - ti.t0;
+    ti.frame_limit = last < 0 ? 0 : (last > TF ? TF : last);
+    const int s0 = ti.t0 * p.hop - p.pad_inner - p.pad_outer;
+    ti.async = row_vec_ok && s0 >= 0 && (s0 & 3) == 0 && s0 + p.wave_len <= p.n_samples;
+    ti.src0 = (long long)ti.row * p.row_stride + s0;
+    return ti;
   };
-  // log-mel output needs every frame; otherwise tiles past the valid length are skipped
-  auto tile_dead = [&](int tile) { return !kLogmel && tile_t0(tile) >= row_valid(tile_row(tile)); };
-  auto tile_async = [&](int tile) {
-    const int s0 = tile_t0(tile) * p.hop - p.pad_inner - p.pad_outer;
-    return row_vec_ok && s0 >= 0 && (s0 & 3) == 0 && s0 + p.wave_len <= p.n_samples;
-  };
-  // Start filling wave buffer b with the samples of `tile`.
-  auto stage = [&](int tile, int b) {
-    if (tile_dead(tile)) return;
+  // Start filling wave buffer b with the samples of a tile.
+  auto stage = [&](const TileInfo& ti, int b) {
+    if (ti.frame_limit == 0) return;
     float* wave = wave0 + b * p.wave_len;
-    const float* src = p.wav + (long long)tile_row(tile) * p.row_stride;
-    const int j0 = tile_t0(tile) * p.hop;  // first position in the padded row
-    if (tile_async(tile)) {
+    if (ti.async) {
       if (tid == 0) {
         fence_proxy_async();  // earlier generic-proxy reads of this buffer are ordered before the async write
         mbar_expect_tx(&bars[b], p.wave_len * 4);
-        bulk_copy_g2s(wave, src + (j0 - p.pad_inner - p.pad_outer), p.wave_len * 4, &bars[b]);
+        bulk_copy_g2s(wave, p.wav + ti.src0, p.wave_len * 4, &bars[b]);
       }
     } else {
+      const float* src = p.wav + (long long)ti.row * p.row_stride;
+      const int j0 = ti.t0 * p.hop;  // first position in the padded row
       for (int i = tid; i < p.wave_len; i += kThreads) {
         const int j = j0 + i;
         float x = 0.f;
@@ -261,150 +273,150 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
 
   __syncthreads();  // constants + barrier init visible
   int tile = blockIdx.x;
-  if (tile < p.n_tiles) stage(tile, 0);
+  TileInfo cur = describe(tile < p.n_tiles ? tile : 0);
+  if (tile < p.n_tiles) stage(cur, 0);
 
   for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
     const int b = it & 1;
-    const int row = tile_row(tile);
-    const int t0 = tile_t0(tile);
-    const int n_valid = row_valid(row);
-    const bool dead = tile_dead(tile);
     const float* wave = wave0 + b * p.wave_len;
+    const bool dead = cur.frame_limit == 0;
 
     // ---- 1. this tile's samples are in wave[b]; start fetching the next tile
     if (!dead) {
-      if (tile_async(tile)) {
+      if (cur.async) {
         mbar_wait(&bars[b], (phase_bits >> b) & 1u);
         phase_bits ^= 1u << b;
       } else {
         __syncthreads();  // plain stores of all threads
       }
     }
-    if (tile + (int)gridDim.x < p.n_tiles) stage(tile + gridDim.x, b ^ 1);
+    const bool has_next = tile + (int)gridDim.x < p.n_tiles;
+    const TileInfo nxt = describe(has_next ? tile + (int)gridDim.x : tile);
+    if (has_next) stage(nxt, b ^ 1);
 
     // ---- 2. FFT -> magnitudes ------------------------------------------------
-    if (!dead) {
-      if constexpr (NFFT == 1024) {
-        const int h = lane >> 4;
-        const int partner = mirror_lane512(lane);
+    if constexpr (NFFT == 1024) {
+      const int h = lane >> 4;
+      const int partner = mirror_lane512(lane);
 #pragma unroll 1
-        for (int fr = warp; fr < TF; fr += kWarps) {
-          const float* fa = wave + fr * p.hop;
-          float2 v[16];
-          if (hop_even) {
-            const float2* f2 = reinterpret_cast<const float2*>(fa);
+      for (int fr = warp; fr < cur.frame_limit; fr += kWarps) {
+        const float* fa = wave + fr * p.hop;
+        float2 v[16];
+        if (hop_even) {
+          const float2* f2 = reinterpret_cast<const float2*>(fa);
 #pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) {
-              const float2 x = f2[32 * n1 + lane];
-              v[n1] = make_float2(x.x * win[n1].x, x.y * win[n1].y);
-            }
-          } else {
-#pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) {
-              const int idx = 2 * (32 * n1 + lane);
-              v[n1] = make_float2(fa[idx] * win[n1].x, fa[idx + 1] * win[n1].y);
-            }
+          for (int n1 = 0; n1 < 16; ++n1) {
+            const float2 x = f2[32 * n1 + lane];
+            v[n1] = make_float2(x.x * win[n1].x, x.y * win[n1].y);
           }
-          __syncwarp();  // previous frame's pass-2 reads of my_tile are done
-          fft512_pass1(v, tw, my_tile, lane);
-          __syncwarp();
-          fft512_pass2(v, my_tile, lane);
-          float2 send[8], recv[8], zlo[8], zhi[8];
-          combine_send(v, h, send);
+        } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            recv[j] = make_float2(__shfl_xor_sync(0xffffffffu, send[j].x, 16), __shfl_xor_sync(0xffffffffu, send[j].y, 16));
-          combine_finish(v, recv, h, zlo, zhi);
-          mirror_send512(zlo, zhi, lane, send);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            recv[j] = make_float2(__shfl_sync(0xffffffffu, send[j].x, partner), __shfl_sync(0xffffffffu, send[j].y, partner));
-          unfold_store512(zlo, zhi, recv, fold_base, mags + fr * kPitch, lane);
-        }
-      } else {
-#pragma unroll 1
-        for (int fr = warp; fr < TF; fr += kWarps) {
-          const float* fa = wave + fr * p.hop;
-          float2 v[32];
-#pragma unroll
-          for (int n1 = 0; n1 < 32; ++n1) {
+          for (int n1 = 0; n1 < 16; ++n1) {
             const int idx = 2 * (32 * n1 + lane);
-            const float2 w = *reinterpret_cast<const float2*>(s_window + idx);
-            v[n1] = make_float2(fa[idx] * w.x, fa[idx + 1] * w.y);
+            v[n1] = make_float2(fa[idx] * win[n1].x, fa[idx + 1] * win[n1].y);
           }
-          __syncwarp();
-          fft1024_pass1(v, tw, my_tile, lane);
-          __syncwarp();
-          fft1024_pass2(v, my_tile, lane);
-          float* mrow = mags + fr * kPitch;
-          const int partner = (32 - lane) & 31;
+        }
+        __syncwarp();  // previous frame's pass-2 reads of my_tile are done
+        fft512_pass1(v, tw, my_tile, lane);
+        __syncwarp();
+        fft512_pass2(v, my_tile, lane);
+        float2 send[8], recv[8], zlo[8], zhi[8];
+        combine_send(v, h, send);
 #pragma unroll
-          for (int k2 = 0; k2 < 16; ++k2) {
-            const float2 send =
-                (lane == 0) ? v[brev5(mirror_slot1024(k2, true))] : v[brev5(mirror_slot1024(k2, false))];
-            const float2 bm = make_float2(__shfl_sync(0xffffffffu, send.x, partner),
-                                          __shfl_sync(0xffffffffu, send.y, partner));
-            const int k = 32 * k2 + lane;
-            float xk, xm;
-            folded_magnitudes(v[brev5(k2)], bm, s_fold[k], xk, xm);
-            mrow[k] = xk;
-            mrow[1024 - k] = xm;
-          }
-          if (lane == 0) {
-            float xk, xm;
-            folded_magnitudes(v[brev5(16)], v[brev5(16)], s_fold[512], xk, xm);
-            mrow[512] = xk;
-          }
+        for (int j = 0; j < 8; ++j)
+          recv[j] = make_float2(__shfl_xor_sync(0xffffffffu, send[j].x, 16), __shfl_xor_sync(0xffffffffu, send[j].y, 16));
+        combine_finish(v, recv, h, zlo, zhi);
+        mirror_send512(zlo, zhi, lane, send);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          recv[j] = make_float2(__shfl_sync(0xffffffffu, send[j].x, partner), __shfl_sync(0xffffffffu, send[j].y, partner));
+        unfold_store512(zlo, zhi, recv, fold_base, mags + fr * kPitch, lane);
+      }
+    } else {
+#pragma unroll 1
+      for (int fr = warp; fr < cur.frame_limit; fr += kWarps) {
+        const float* fa = wave + fr * p.hop;
+        float2 v[32];
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const int idx = 2 * (32 * n1 + lane);
+          const float2 w = *reinterpret_cast<const float2*>(s_window + idx);
+          v[n1] = make_float2(fa[idx] * w.x, fa[idx + 1] * w.y);
+        }
+        __syncwarp();
+        fft1024_pass1(v, tw, my_tile, lane);
+        __syncwarp();
+        fft1024_pass2(v, my_tile, lane);
+        float* mrow = mags + fr * kPitch;
+        const int partner = (32 - lane) & 31;
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+          const float2 send =
+              (lane == 0) ? v[brev5(mirror_slot1024(k2, true))] : v[brev5(mirror_slot1024(k2, false))];
+          const float2 bm = make_float2(__shfl_sync(0xffffffffu, send.x, partner),
+                                        __shfl_sync(0xffffffffu, send.y, partner));
+          const int k = 32 * k2 + lane;
+          float xk, xm;
+          folded_magnitudes(v[brev5(k2)], bm, s_fold[k], xk, xm);
+          mrow[k] = xk;
+          mrow[1024 - k] = xm;
+        }
+        if (lane == 0) {
+          float xk, xm;
+          folded_magnitudes(v[brev5(16)], v[brev5(16)], s_fold[512], xk, xm);
+          mrow[512] = xk;
         }
       }
     }
     __syncthreads();
 
     // ---- 3. mel filterbank, log, quantise --------------------------------
+    // One lane per frame, 32/TF adjacent channels side by side in a warp.  The host pads the spans
+    // of such a channel group to one common length, so the bin loop is warp-uniform.
     {
-      constexpr int kGroups = 32 / TF;  // channels handled side by side in one warp
+      constexpr int kGroups = 32 / TF;
       const int fr = lane % TF;
       const int sub = lane / TF;
-      const int t = t0 + fr;
+      const int t = cur.t0 + fr;
       const bool in_row = t < p.n_frames;
-      const bool valid = t < n_valid;
+      const bool valid = t < cur.n_valid;
       const float* mrow = mags + fr * kPitch;
-      const size_t out0 = (size_t)row * p.n_mels * p.n_frames + t;
+      const size_t out0 = (size_t)cur.row * p.n_mels * p.n_frames + t;
       const float kmax = float(p.n_bins - 1);
-      // the channel loop is warp-uniform (shuffles inside); a group past the last channel idles
 #pragma unroll 1
-      for (int mb = warp * kGroups; mb < p.n_mels; mb += kWarps * kGroups) {
+      for (int mb = warp * kGroups; mb < p.n_chan_pad; mb += kWarps * kGroups) {
         const int m = mb + sub;
         const bool live = m < p.n_mels;
         float value = 0.f;
-        if (live && !dead) {
+        if (!dead) {
           const int4 c = s_chan[m];
           const float4* w4 = reinterpret_cast<const float4*>(s_weights + c.z);
-          const float* x = mrow + c.x;
+          const float4* x4 = reinterpret_cast<const float4*>(mrow + c.x);
+          const int n4 = c.y >> 2;  // >= 1, identical for every lane of the warp
           float acc = 0.f;
-          for (int i = 0; i < c.y; i += 4) {
-            const float4 w = w4[i >> 2];
-            acc = fmaf(w.x, x[i], acc);
-            acc = fmaf(w.y, x[i + 1], acc);
-            acc = fmaf(w.z, x[i + 2], acc);
-            acc = fmaf(w.w, x[i + 3], acc);
+#pragma unroll 1
+          for (int i = 0; i < n4; ++i) {
+            const float4 w = w4[i];
+            const float4 x = x4[i];
+            acc = fmaf(w.x, x.x, acc);
+            acc = fmaf(w.y, x.y, acc);
+            acc = fmaf(w.z, x.z, acc);
+            acc = fmaf(w.w, x.w, acc);
           }
-          value = __logf(fmaxf(acc, kLogClip));
+          value = fast_log(fmaxf(acc, kLogClip));
         }
         const size_t o = out0 + (size_t)m * p.n_frames;
         if constexpr (kLogmel) {
           if (live && in_row) p.logmel[o] = value;
         }
         if constexpr (kCodes) {
-          if (live && in_row) {
-            const float sc = s_scale[m];
-            const float pos = __fmul_rn(__fsub_rn(value, s_lo[m]), sc);
-            const float q = fminf(fmaxf(floorf(pos), 0.f), kmax);
-            p.codes[o] = valid ? (unsigned char)q : (unsigned char)0;
-            if constexpr (kEdge) {
-              const float e = fminf(fmaxf(rintf(pos), 1.f), kmax);
-              if (valid && fabsf(pos - e) < p.edge_eps * sc) ++edge_hits;
-            }
+          const float sc = s_scale[m];
+          const float pos = __fmul_rn(__fsub_rn(value, s_lo[m]), sc);
+          const float q = fminf(fmaxf(floorf(pos), 0.f), kmax);
+          if (live && in_row) p.codes[o] = valid ? (unsigned char)q : (unsigned char)0;
+          if constexpr (kEdge) {
+            const float e = fminf(fmaxf(rintf(pos), 1.f), kmax);
+            if (live && valid && fabsf(pos - e) < p.edge_eps * sc) ++edge_hits;
           }
         }
         if constexpr (kStats) {
@@ -423,6 +435,7 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
       }
     }
     __syncthreads();  // mags and wave[b] are free again
+    cur = nxt;
   }
 
   // ---- flush per-CTA statistics -------------------------------------------
