@@ -23,6 +23,7 @@ SIGNATURES = {
     "dmel_last_error": (c_char_p, []),
     "dmel_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, POINTER(c_void_p)]),
     "dmel_plan_destroy": (None, [c_void_p]),
+    "dmel_plan_describe": (c_int, [c_void_p, c_char_p, ctypes.c_size_t]),
     "dmel_plan_num_frames": (c_longlong, [c_void_p, c_longlong]),
     "dmel_logmel_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_void_p, c_void_p]),
     "dmel_minmax_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_void_p,

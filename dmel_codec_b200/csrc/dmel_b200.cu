@@ -63,7 +63,7 @@ struct dmel_plan {
   float* d_window = nullptr;
   float2* d_stage_tw = nullptr;
   float2* d_fold_tw = nullptr;
-  int4* d_chan = nullptr;
+  int2* d_chan = nullptr;
   float* d_weights = nullptr;
   // scratch for the host-buffer entry point (grown on demand)
   cudaStream_t streams[2] = {nullptr, nullptr};
@@ -129,10 +129,10 @@ cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int gr
 // loads).  `group` adjacent channels are evaluated side by side in one warp, so their spans are
 // zero-padded to one common length (a multiple of 4, at least 4) and phantom channels complete
 // the last group; the bin loop is then uniform across the warp.
-void band_filterbank(const float* basis, int n_mels, int n_freq, int group, std::vector<int4>* chan,
+void band_filterbank(const float* basis, int n_mels, int n_freq, int group, std::vector<int2>* chan,
                      std::vector<float>* weights) {
   const int n_pad = (n_mels + group - 1) / group * group;
-  chan->assign(n_pad, make_int4(0, 4, 0, 0));
+  chan->assign(n_pad, make_int2(4 << 16, 0));
   weights->clear();
   std::vector<int> first(n_pad, 0), last(n_pad, -1);
   for (int m = 0; m < n_mels; ++m) {
@@ -152,7 +152,7 @@ void band_filterbank(const float* basis, int n_mels, int n_freq, int group, std:
     const int pitch = n_freq + 3;  // FusedLayout::kMagPitch, a multiple of 4
     for (int m = g; m < g + group; ++m) {
       first[m] = std::min(first[m], pitch - count);  // keep the padded span inside the frame's row
-      (*chan)[m] = make_int4(first[m], count, (int)weights->size(), 0);
+      (*chan)[m] = make_int2(first[m] | (count << 16), (int)weights->size());
       for (int i = 0; i < count; ++i) {
         const int f = first[m] + i;
         weights->push_back((m < n_mels && f >= 0 && f <= last[m]) ? basis[(size_t)m * n_freq + f] : 0.f);
@@ -284,7 +284,7 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
   DMEL_CUDA(cudaDeviceGetAttribute(&max_sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, plan->device));
   const size_t half_sm = (size_t)max_sm_smem / 2 - 1024;  // 1 KB per CTA is reserved by the driver
   const int candidates[2] = {16, 8};
-  std::vector<int4> chan;
+  std::vector<int2> chan;
   std::vector<float> weights;
   for (int pass = 0; pass < 2 && !plan->tile_frames; ++pass)
     for (int tf : candidates) {
@@ -352,6 +352,17 @@ void dmel_plan_destroy(dmel_plan* plan) {
   cudaFree(plan->d_lo);
   cudaFree(plan->d_scale);
   delete plan;
+}
+
+int dmel_plan_describe(const dmel_plan* plan, char* buf, size_t buf_len) {
+  if (!plan || !buf || buf_len == 0) return fail(DMEL_ERR_INVALID, "plan / buf is null");
+  snprintf(buf, buf_len,
+           "{\"n_fft\": %d, \"hop\": %d, \"n_mels\": %d, \"center\": %d, \"tile_frames\": %d, "
+           "\"ctas_per_sm\": %d, \"smem_bytes\": %zu, \"banded_weights\": %d, \"n_chan_pad\": %d, "
+           "\"wave_len\": %d, \"sm_count\": %d}",
+           plan->n_fft, plan->hop, plan->n_mels, plan->center, plan->tile_frames, plan->ctas_per_sm,
+           plan->smem_bytes, plan->nnz, plan->n_chan_pad, plan->wave_len, plan->sm_count);
+  return DMEL_OK;
 }
 
 long long dmel_plan_num_frames(const dmel_plan* plan, long long n_samples) {

@@ -52,7 +52,7 @@ struct FusedParams {
   const float* window;      // (n_fft)
   const float2* stage_tw;   // n_fft 1024: [16][32] W_512^{k1*n2}; n_fft 2048: [32][32] W_1024^{k1*n2}
   const float2* fold_tw;    // [n_fft/4 + 1]: W_{n_fft}^k
-  const int4* chan;         // (n_chan_pad) {first bin (mult. of 4), count (mult. of 4, same within a group), weight offset, 0}
+  const int2* chan;         // (n_chan_pad) {first bin | count << 16 (both mult. of 4, count equal within a group), weight offset}
   const float* weights;
   const int* lengths;       // valid samples per row, or null
   float* logmel;            // (B, M, T)            [kOutLogmel]
@@ -121,9 +121,9 @@ struct FusedLayout {
   static constexpr int kBins = NFFT / 2 + 1;
   // row pitch 516 / 1028 floats: a multiple of 4 so a lane can fetch four bins of its frame with
   // one LDS.128, and == 4 (mod 32) so the eight lanes of a quarter-warp (eight frames) cover all
-  // 32 banks.  64 floats of zeroed tail: a group's common span length may run past its last row.
+  // 32 banks.  The host keeps every padded span inside its row.
   static constexpr int kMagPitch = kBins + 3;
-  static constexpr int kMagFloats = TF * kMagPitch + 64;
+  static constexpr int kMagFloats = TF * kMagPitch;
   static constexpr int kTileF2 = NFFT == 1024 ? kTile512 : kTile1024;
   static constexpr int kFoldN = NFFT / 4 + 1;
   // byte offsets inside dynamic shared memory (all 16-byte aligned)
@@ -140,13 +140,13 @@ struct FusedLayout {
   }
   // n_chan = channel count padded to the group size
   static __host__ __device__ size_t weights_off(int wave_len, int n_chan) {
-    return align16(chan_off(wave_len) + size_t(n_chan) * 16);
+    return align16(chan_off(wave_len) + size_t(n_chan) * 8);
   }
   static __host__ __device__ size_t perchan_off(int wave_len, int n_chan, int nnz) {
     return align16(weights_off(wave_len, n_chan) + size_t(nnz) * 4);
   }
   static __host__ __device__ size_t bar_off(int wave_len, int n_chan, int nnz) {
-    return align16(perchan_off(wave_len, n_chan, nnz) + size_t(n_chan) * 16);  // lo, scale, min, max
+    return align16(perchan_off(wave_len, n_chan, nnz) + size_t(n_chan) * 8);  // {lo, scale} or {min, max}
   }
   static __host__ __device__ size_t total(int wave_len, int n_chan, int nnz) {
     return bar_off(wave_len, n_chan, nnz) + 16;
@@ -176,12 +176,15 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
   float* wave0 = reinterpret_cast<float*>(smem + LY::wave_off());
   float* s_window = reinterpret_cast<float*>(smem + LY::window_off(p.wave_len));
   float2* s_fold = reinterpret_cast<float2*>(smem + LY::fold_off(p.wave_len));
-  int4* s_chan = reinterpret_cast<int4*>(smem + LY::chan_off(p.wave_len));
+  int2* s_chan = reinterpret_cast<int2*>(smem + LY::chan_off(p.wave_len));
   float* s_weights = reinterpret_cast<float*>(smem + LY::weights_off(p.wave_len, p.n_chan_pad));
+  // two per-channel arrays: quantiser {lo, scale} when writing codes, running {min, max} when
+  // calibrating (no launch does both)
+  static_assert(!(kCodes && kStats), "codes and statistics share their per-channel scratch");
   float* s_lo = reinterpret_cast<float*>(smem + LY::perchan_off(p.wave_len, p.n_chan_pad, p.nnz));
   float* s_scale = s_lo + p.n_chan_pad;
-  float* s_min = s_scale + p.n_chan_pad;
-  float* s_max = s_min + p.n_chan_pad;
+  float* s_min = s_lo;
+  float* s_max = s_scale;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LY::bar_off(p.wave_len, p.n_chan_pad, p.nnz));
 
   const int tid = threadIdx.x;
@@ -192,14 +195,17 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
   // ---- per-CTA constants -------------------------------------------------
   for (int i = tid; i < p.n_chan_pad; i += kThreads) {
     s_chan[i] = p.chan[i];
-    const bool real = i < p.n_mels;
-    s_lo[i] = (kCodes && real) ? p.q_lo[i] : 0.f;
-    s_scale[i] = (kCodes && real) ? p.q_scale[i] : 0.f;
-    s_min[i] = __int_as_float(0x7f800000);
-    s_max[i] = __int_as_float(0xff800000);
+    if constexpr (kCodes) {
+      const bool real = i < p.n_mels;
+      s_lo[i] = real ? p.q_lo[i] : 0.f;
+      s_scale[i] = real ? p.q_scale[i] : 0.f;
+    } else {
+      s_min[i] = __int_as_float(0x7f800000);
+      s_max[i] = __int_as_float(0xff800000);
+    }
   }
   for (int i = tid; i < p.nnz; i += kThreads) s_weights[i] = p.weights[i];
-  for (int i = tid; i < LY::kMagFloats; i += kThreads) mags[i] = 0.f;  // pad columns and tail stay zero
+  for (int i = tid; i < LY::kMagFloats; i += kThreads) mags[i] = 0.f;  // the 3 pad columns of each row stay zero
   if constexpr (NFFT == 2048) {
     for (int i = tid; i < NFFT; i += kThreads) s_window[i] = p.window[i];
     for (int i = tid; i < LY::kFoldN; i += kThreads) s_fold[i] = p.fold_tw[i];
@@ -389,10 +395,10 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
         const bool live = m < p.n_mels;
         float value = 0.f;
         if (!dead) {
-          const int4 c = s_chan[m];
-          const float4* w4 = reinterpret_cast<const float4*>(s_weights + c.z);
-          const float4* x4 = reinterpret_cast<const float4*>(mrow + c.x);
-          const int n4 = c.y >> 2;  // >= 1, identical for every lane of the warp
+          const int2 c = s_chan[m];
+          const float4* w4 = reinterpret_cast<const float4*>(s_weights + c.y);
+          const float4* x4 = reinterpret_cast<const float4*>(mrow + (c.x & 0xffff));
+          const int n4 = c.x >> 18;  // span length / 4: >= 1, identical for every lane of the warp
           float acc = 0.f;
 #pragma unroll 1
           for (int i = 0; i < n4; ++i) {

@@ -73,6 +73,13 @@ class Plan:
                 pass
             self._handle = ctypes.c_void_p()
 
+    def describe(self) -> dict:
+        """Launch configuration the library chose for this geometry (diagnostics)."""
+        import json
+        buf = ctypes.create_string_buffer(512)
+        _native.check(_native.load().dmel_plan_describe(self._handle, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     def num_frames(self, n_samples: int) -> int:
         return int(_native.load().dmel_plan_num_frames(self._handle, int(n_samples)))
 

@@ -55,6 +55,10 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center,
                      dmel_plan** out);
 void dmel_plan_destroy(dmel_plan* plan);
 
+/* Writes a one-line JSON description of the launch configuration chosen for this geometry
+ * (frame tile, CTAs per SM, shared memory, banded filterbank size) into buf. Diagnostics only. */
+int dmel_plan_describe(const dmel_plan* plan, char* buf, size_t buf_len);
+
 /* T for a row of n_samples (reference: shape of the torch.stft output, :64-75);
  * <= 0 when the row is too short.  n_samples must exceed the reflect pad. */
 long long dmel_plan_num_frames(const dmel_plan* plan, long long n_samples);

@@ -93,6 +93,14 @@ def test_logmel_vs_oracle_other_geometries(d, kw):
     assert ok, f"{ratio:.2f}x tolerance"
 
 
+def test_launch_configuration_for_the_benchmark_geometry(d):
+    """configs[1] must get the 16-frame tile with two CTAs per SM (shared memory is sized to the byte for it)."""
+    tr = _transform(d, GOLDEN_GEOMETRY["cfg2_24k_128"])
+    info = tr.spectrogram.plan_for(torch.device("cuda", torch.cuda.current_device())).describe()
+    assert info["tile_frames"] == 16 and info["ctas_per_sm"] == 2, info
+    assert info["smem_bytes"] <= 115712
+
+
 def test_too_short_input_raises_like_the_reference(d):
     tr = _transform(d, GOLDEN_GEOMETRY["cfg1_16k_80"])
     with pytest.raises(ValueError, match="reflect"):
