@@ -84,6 +84,24 @@ size_t fused_smem(int wave_len, int n_mels, int nnz) {
   return dmel::FusedLayout<NFFT, TF>::total(wave_len, n_mels, nnz);
 }
 
+template <int NFFT, int TF>
+void fill_offsets(FusedParams* p) {
+  using LY = dmel::FusedLayout<NFFT, TF>;
+  p->off_mags = (int)LY::mags_off();
+  p->off_wave = (int)LY::wave_off();
+  p->off_window = (int)LY::window_off(p->wave_len);
+  p->off_fold = (int)LY::fold_off(p->wave_len);
+  p->off_chan = (int)LY::chan_off(p->wave_len);
+  p->off_weights = (int)LY::weights_off(p->wave_len, p->n_chan_pad);
+  p->off_perchan = (int)LY::perchan_off(p->wave_len, p->n_chan_pad, p->nnz);
+  p->off_bars = (int)LY::bar_off(p->wave_len, p->n_chan_pad, p->nnz);
+}
+
+void fill_offsets_for(int n_fft, int tf, FusedParams* p) {
+  if (n_fft == 1024) return tf == 16 ? fill_offsets<1024, 16>(p) : fill_offsets<1024, 8>(p);
+  return tf == 16 ? fill_offsets<2048, 16>(p) : fill_offsets<2048, 8>(p);
+}
+
 size_t fused_smem_for(int n_fft, int tf, int wave_len, int n_mels, int nnz) {
   if (n_fft == 1024) return tf == 16 ? fused_smem<1024, 16>(wave_len, n_mels, nnz) : fused_smem<1024, 8>(wave_len, n_mels, nnz);
   return tf == 16 ? fused_smem<2048, 16>(wave_len, n_mels, nnz) : fused_smem<2048, 8>(wave_len, n_mels, nnz);
@@ -207,6 +225,8 @@ int prepare_fused(dmel_plan* plan, const float* wav, long long n_rows, long long
   p->chan = plan->d_chan;
   p->weights = plan->d_weights;
   p->n_bins = 1;
+  p->kmax = 0.f;
+  fill_offsets_for(plan->n_fft, plan->tile_frames, p);
   *grid = (int)std::min<long long>(n_tiles, (long long)plan->sm_count * plan->ctas_per_sm);
   return DMEL_OK;
 }
@@ -416,6 +436,7 @@ int dmel_encode_u8(dmel_plan* plan, const float* wav_dev, long long n_rows, long
   p.q_lo = lo_dev;
   p.q_scale = scale_dev;
   p.n_bins = n_bins;
+  p.kmax = float(n_bins - 1);
   p.codes = codes_dev;
   p.logmel = logmel_dev;
   p.near_edge = near_edge_dev;

@@ -60,6 +60,10 @@ struct FusedParams {
   const float* q_lo;        // (M)                  [kOutCodes]
   const float* q_scale;     // (M)  K / (hi - lo)   [kOutCodes]
   int n_bins;
+  float kmax;               // float(n_bins - 1)
+  // byte offsets of the shared-memory regions (FusedLayout, filled in by the host so the kernel
+  // does no layout arithmetic)
+  int off_mags, off_wave, off_window, off_fold, off_chan, off_weights, off_perchan, off_bars;
   float* run_min;           // (M) running min, updated in place [kOutStats]
   float* run_max;           // (M)
   unsigned long long* near_edge;  // [kOutEdge]
@@ -171,21 +175,21 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
   constexpr bool kStats = (MODE & kOutStats) != 0, kEdge = (MODE & kOutEdge) != 0;
 
   extern __shared__ __align__(16) unsigned char smem[];
-  float2* tiles = reinterpret_cast<float2*>(smem + LY::tiles_off());
-  float* mags = reinterpret_cast<float*>(smem + LY::mags_off());
-  float* wave0 = reinterpret_cast<float*>(smem + LY::wave_off());
-  float* s_window = reinterpret_cast<float*>(smem + LY::window_off(p.wave_len));
-  float2* s_fold = reinterpret_cast<float2*>(smem + LY::fold_off(p.wave_len));
-  int2* s_chan = reinterpret_cast<int2*>(smem + LY::chan_off(p.wave_len));
-  float* s_weights = reinterpret_cast<float*>(smem + LY::weights_off(p.wave_len, p.n_chan_pad));
+  float2* tiles = reinterpret_cast<float2*>(smem);
+  float* mags = reinterpret_cast<float*>(smem + p.off_mags);
+  float* wave0 = reinterpret_cast<float*>(smem + p.off_wave);
+  float* s_window = reinterpret_cast<float*>(smem + p.off_window);
+  float2* s_fold = reinterpret_cast<float2*>(smem + p.off_fold);
+  int2* s_chan = reinterpret_cast<int2*>(smem + p.off_chan);
+  float* s_weights = reinterpret_cast<float*>(smem + p.off_weights);
   // two per-channel arrays: quantiser {lo, scale} when writing codes, running {min, max} when
   // calibrating (no launch does both)
   static_assert(!(kCodes && kStats), "codes and statistics share their per-channel scratch");
-  float* s_lo = reinterpret_cast<float*>(smem + LY::perchan_off(p.wave_len, p.n_chan_pad, p.nnz));
+  float* s_lo = reinterpret_cast<float*>(smem + p.off_perchan);
   float* s_scale = s_lo + p.n_chan_pad;
   float* s_min = s_lo;
   float* s_max = s_scale;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LY::bar_off(p.wave_len, p.n_chan_pad, p.nnz));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -381,61 +385,71 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
     // of such a channel group to one common length, so the bin loop is warp-uniform.
     {
       constexpr int kGroups = 32 / TF;
+      constexpr int kStep = kWarps * kGroups;  // channels between two trips of a lane
       const int fr = lane % TF;
       const int sub = lane / TF;
       const int t = cur.t0 + fr;
       const bool in_row = t < p.n_frames;
       const bool valid = t < cur.n_valid;
       const float* mrow = mags + fr * kPitch;
-      const size_t out0 = (size_t)cur.row * p.n_mels * p.n_frames + t;
-      const float kmax = float(p.n_bins - 1);
+      const int m0 = warp * kGroups + sub;
+      const size_t ostep = (size_t)kStep * p.n_frames;
+      size_t o = ((size_t)cur.row * p.n_mels + m0) * p.n_frames + t;
+      if (dead) {
+        // nothing of this tile is valid audio: codes are the pad value, nothing else is written
+        if constexpr (kCodes) {
 #pragma unroll 1
-      for (int mb = warp * kGroups; mb < p.n_chan_pad; mb += kWarps * kGroups) {
-        const int m = mb + sub;
-        const bool live = m < p.n_mels;
-        float value = 0.f;
-        if (!dead) {
-          const int2 c = s_chan[m];
+          for (int m = m0; m < p.n_mels; m += kStep, o += ostep)
+            if (in_row) p.codes[o] = 0;
+        }
+      } else {
+        const int2* cp = s_chan + m0;
+        const float* lop = s_lo + m0;
+        const float* scp = s_scale + m0;
+#pragma unroll 1
+        for (int mb = warp * kGroups; mb < p.n_chan_pad; mb += kStep, cp += kStep, lop += kStep, scp += kStep, o += ostep) {
+          const int m = mb + sub;
+          const bool live = m < p.n_mels;
+          const int2 c = *cp;
           const float4* w4 = reinterpret_cast<const float4*>(s_weights + c.y);
           const float4* x4 = reinterpret_cast<const float4*>(mrow + (c.x & 0xffff));
-          const int n4 = c.x >> 18;  // span length / 4: >= 1, identical for every lane of the warp
+          const float4* x4_end = x4 + (c.x >> 18);  // span length / 4: >= 1, identical across the warp
           float acc = 0.f;
 #pragma unroll 1
-          for (int i = 0; i < n4; ++i) {
-            const float4 w = w4[i];
-            const float4 x = x4[i];
+          do {
+            const float4 w = *w4++;
+            const float4 x = *x4++;
             acc = fmaf(w.x, x.x, acc);
             acc = fmaf(w.y, x.y, acc);
             acc = fmaf(w.z, x.z, acc);
             acc = fmaf(w.w, x.w, acc);
+          } while (x4 != x4_end);
+          const float value = fast_log(fmaxf(acc, kLogClip));
+          if constexpr (kLogmel) {
+            if (live && in_row) p.logmel[o] = value;
           }
-          value = fast_log(fmaxf(acc, kLogClip));
-        }
-        const size_t o = out0 + (size_t)m * p.n_frames;
-        if constexpr (kLogmel) {
-          if (live && in_row) p.logmel[o] = value;
-        }
-        if constexpr (kCodes) {
-          const float sc = s_scale[m];
-          const float pos = __fmul_rn(__fsub_rn(value, s_lo[m]), sc);
-          const float q = fminf(fmaxf(floorf(pos), 0.f), kmax);
-          if (live && in_row) p.codes[o] = valid ? (unsigned char)q : (unsigned char)0;
-          if constexpr (kEdge) {
-            const float e = fminf(fmaxf(rintf(pos), 1.f), kmax);
-            if (live && valid && fabsf(pos - e) < p.edge_eps * sc) ++edge_hits;
+          if constexpr (kCodes) {
+            const float sc = *scp;
+            const float pos = __fmul_rn(__fsub_rn(value, *lop), sc);
+            const float q = fminf(fmaxf(floorf(pos), 0.f), p.kmax);
+            if (live && in_row) p.codes[o] = valid ? (unsigned char)q : (unsigned char)0;
+            if constexpr (kEdge) {
+              const float e = fminf(fmaxf(rintf(pos), 1.f), p.kmax);
+              if (live && valid && fabsf(pos - e) < p.edge_eps * sc) ++edge_hits;
+            }
           }
-        }
-        if constexpr (kStats) {
-          float lo = (valid && live) ? value : __int_as_float(0x7f800000);
-          float hi = (valid && live) ? value : __int_as_float(0xff800000);
+          if constexpr (kStats) {
+            float lo = (valid && live) ? value : __int_as_float(0x7f800000);
+            float hi = (valid && live) ? value : __int_as_float(0xff800000);
 #pragma unroll
-          for (int d = TF / 2; d >= 1; d >>= 1) {
-            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
-          }
-          if (fr == 0 && live) {  // channel m always belongs to this lane of this warp: no race
-            s_min[m] = fminf(s_min[m], lo);
-            s_max[m] = fmaxf(s_max[m], hi);
+            for (int d = TF / 2; d >= 1; d >>= 1) {
+              lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+              hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+            }
+            if (fr == 0 && live) {  // channel m always belongs to this lane of this warp: no race
+              s_min[m] = fminf(s_min[m], lo);
+              s_max[m] = fmaxf(s_max[m], hi);
+            }
           }
         }
       }
