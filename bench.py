@@ -165,6 +165,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     q = tok.quantizer
     plan = tok._plan(dev)
     lo, scale, table = q.lo, q.scale(), q.table()
+    launch_cfg = plan.describe()
     torch.cuda.synchronize()
 
     from dmel_codec_b200 import plan as P
@@ -258,7 +259,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "config": {"workload": WORKLOAD, "per_gpu_batch": f"{BATCH}x{SECONDS}s", "sharding": "utterances, no data-path collective",
                    "l2": f"inputs cycle through a ring of {RING} distinct batches ({RING * ENCODE_BYTES / 1e6:.0f} MB > 126 MB L2)",
                    "wall_ms_per_step": wall_ms / args.steps},
-        "roofline": {"bound": "hbm", "kernel": "dmel_fused_kernel<1024,32> (encode)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": f"dmel_fused_kernel<{GEOM['n_fft']},{launch_cfg['tile_frames']},codes> "
+                     f"({launch_cfg['ctas_per_sm']} CTA/SM, {launch_cfg['smem_bytes']} B smem)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ENCODE_BYTES, "avg_launch_ms": enc_avg_s * 1e3,
                      "dequant": {"achieved": deq_gbs, "frac": deq_gbs / peak, "algorithmic_bytes_per_launch": DEQUANT_BYTES,

@@ -1,0 +1,62 @@
+"""Multi-GPU plumbing of the dMel path: one process per GPU, utterances sharded
+across ranks, and exactly one collective — the min/max all-reduce that turns
+per-shard calibration statistics into dataset-wide bin edges.
+
+Encode itself needs no communication: frames and utterances are independent.
+The reference has no direct collectives either (Lightning DDP only, reference
+config/codec/dMel_used.yaml:18); its per-rank data split is by the lhotse
+sampler (reference dataset/lhotse_tts_dataset.py:184-191).
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, Iterator, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> range:
+    """Contiguous block of item ids owned by ``rank``; blocks differ by at most
+    one item and cover ``range(n_items)`` exactly once."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    base, extra = divmod(n_items, world_size)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def batches(ids: Sequence[int], batch_size: int) -> Iterator[Sequence[int]]:
+    for i in range(0, len(ids), batch_size):
+        yield ids[i:i + batch_size]
+
+
+@torch.no_grad()
+def calibrate_sharded(tokenizer, n_utterances: int, load_batch: Callable[[Sequence[int]], object],
+                      batch_size: int, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Dataset-wide calibration: every rank scans its block of utterance ids
+    (``load_batch(ids)`` returns audios or (audios, audio_lengths) on this
+    rank's GPU), then lo/hi are all-reduced (MIN / MAX).  Exact and order
+    independent, so the result is bit-identical for any number of ranks."""
+    rank, size = world()
+    mine = shard_range(n_utterances, rank, size)
+    tokenizer.calibrate((load_batch(ids) for ids in batches(mine, batch_size)), group=group)
+    return tokenizer.quantizer.lo, tokenizer.quantizer.hi
+
+
+@torch.no_grad()
+def encode_sharded(tokenizer, n_utterances: int, load_batch: Callable[[Sequence[int]], object],
+                   batch_size: int) -> Iterable[Tuple[Sequence[int], torch.Tensor, Optional[torch.Tensor]]]:
+    """Yield (utterance ids, codes, code_lengths) for this rank's block. No communication."""
+    rank, size = world()
+    for ids in batches(shard_range(n_utterances, rank, size), batch_size):
+        item = load_batch(ids)
+        audios, lengths = item if isinstance(item, (tuple, list)) else (item, None)
+        codes, code_lengths = tokenizer.encode(audios, lengths)
+        yield ids, codes, code_lengths

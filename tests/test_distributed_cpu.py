@@ -1,0 +1,75 @@
+"""world_size-2 gloo tests (CPU) of the N>1 host logic: utterance sharding and
+the calibration all-reduce.  The per-shard statistics come from the oracle (the
+CUDA kernels cannot run here); what is under test is that sharding covers every
+utterance once and that MIN/MAX all-reduce of shard statistics is bit-identical
+to single-process calibration."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import GOLDEN_GEOMETRY, oracle_config
+from dmel_codec_b200 import distributed as D
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 8, 10000, 10001):
+        for w in (1, 2, 3, 8):
+            got = [i for r in range(w) for i in D.shard_range(n, r, w)]
+            assert got == list(range(n))
+            sizes = [len(D.shard_range(n, r, w)) for r in range(w)]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        D.shard_range(4, 2, 2)
+    assert [list(b) for b in D.batches(range(5), 2)] == [[0, 1], [2, 3], [4]]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world_size, port, n_utts, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        import dmel_codec_b200 as d
+        from dmel_codec_b200 import synth
+        from oracle import dmel_oracle as O
+        kw = GOLDEN_GEOMETRY["cfg1_16k_80"]
+        cfg = oracle_config(kw)
+        assert D.world() == (rank, world_size)
+        mine = D.shard_range(n_utts, rank, world_size)
+        q = d.DMelQuantizer(kw["n_mels"], 16)  # CPU buffers: gloo reduces them in place
+        for ids in D.batches(mine, 3):
+            lengths = torch.tensor([6000 + 500 * (i % 4) for i in ids])
+            wav = synth.batch(ids, 8000, 16000, "speech", lengths=lengths.tolist())
+            mel = O.log_mel(wav, cfg)
+            lo, hi = O.calibrate_minmax(mel, O.valid_frames(lengths, cfg.hop_length))
+            q.set_stats(torch.minimum(q.lo, lo), torch.maximum(q.hi, hi))
+        q.sync_stats()
+        torch.save({"lo": q.lo, "hi": q.hi, "n": len(mine)}, os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_calibration_allreduce_is_bit_identical(tmp_path):
+    from dmel_codec_b200 import synth
+    from oracle import dmel_oracle as O
+    n_utts, world_size = 10, 2
+    mp.spawn(_worker, args=(world_size, _free_port(), n_utts, str(tmp_path)), nprocs=world_size, join=True)
+    kw = GOLDEN_GEOMETRY["cfg1_16k_80"]
+    cfg = oracle_config(kw)
+    ids = list(range(n_utts))
+    lengths = torch.tensor([6000 + 500 * (i % 4) for i in ids])
+    mel = O.log_mel(synth.batch(ids, 8000, 16000, "speech", lengths=lengths.tolist()), cfg)
+    lo, hi = O.calibrate_minmax(mel, O.valid_frames(lengths, cfg.hop_length))
+    got = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world_size)]
+    assert sum(g["n"] for g in got) == n_utts
+    for g in got:
+        assert torch.equal(g["lo"], lo) and torch.equal(g["hi"], hi)
