@@ -68,7 +68,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -126,7 +126,9 @@ def run_reference(args, rank: int):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     wav, cfg, bank, lo, hi = cpu_oracle_setup(BATCH)
-    for _ in range(args.warmup):
+    steps = min(args.steps, 100)  # each step is a full 64 x 10 s batch on the CPU (~0.1 s): bounded
+    args.steps = steps
+    for _ in range(min(args.warmup, 3)):
         oracle_step(wav, cfg, bank, lo, hi)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -278,8 +280,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: leave out the CPU-baseline leg")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: leave out the host-buffer leg")

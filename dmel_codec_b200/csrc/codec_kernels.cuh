@@ -11,6 +11,29 @@ namespace dmel {
 constexpr int kStreamThreads = 256;
 constexpr int kStreamUnroll = 4;  // groups of 4 elements per thread per trip
 
+// Exact unsigned division of e < 2^31 by a fixed d via one multiply-high and a shift
+// (round-up method: mul = floor(2^(31+s)/d) + 1 with s = ceil(log2 d)); the flat-indexed
+// kernels below need (e / T) and (row % M) per 4 elements and were issue-bound on the
+// hardware divide sequence.
+struct FastDiv {
+  unsigned mul, shift, d;
+  __host__ static FastDiv make(unsigned d) {
+    FastDiv f;
+    f.d = d;
+    if (d <= 1) {
+      f.mul = 0;
+      f.shift = 0;
+      return f;
+    }
+    unsigned s = 0;
+    while ((1ull << s) < d) ++s;
+    f.mul = (unsigned)(((1ull << (31 + s)) / d) + 1);
+    f.shift = s - 1;
+    return f;
+  }
+  __device__ __forceinline__ unsigned div(unsigned e) const { return d <= 1 ? e : (__umulhi(e, mul) >> shift); }
+};
+
 // ---------------------------------------------------------------------------
 // codes (uint8) -> bin centres (float32) by table lookup.  The table is built
 // by the host with the oracle's exact op order, so the result is bit exact by
@@ -18,7 +41,8 @@ constexpr int kStreamUnroll = 4;  // groups of 4 elements per thread per trip
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kStreamThreads) dequantize_kernel(
     const uint8_t* __restrict__ codes, float* __restrict__ out, const float* __restrict__ table,
-    unsigned n_elems, unsigned n_frames, unsigned n_mels, unsigned n_bins, bool vec_ok) {
+    unsigned n_elems, FastDiv by_frames, FastDiv by_mels, unsigned n_bins, bool vec_ok) {
+  const unsigned n_frames = by_frames.d, n_mels = by_mels.d;
   const unsigned groups = n_elems >> 2;
   const unsigned stride = gridDim.x * kStreamThreads;
   const unsigned kmax = n_bins - 1;
@@ -35,9 +59,9 @@ __global__ void __launch_bounds__(kStreamThreads) dequantize_kernel(
         const unsigned g = g0 + u * stride;
         if (g >= groups) continue;
         const unsigned e = g << 2;
-        unsigned rowi = e / n_frames;
+        const unsigned rowi = by_frames.div(e);
         unsigned t = e - rowi * n_frames;
-        unsigned m = rowi % n_mels;
+        unsigned m = rowi - by_mels.div(rowi) * n_mels;
         const unsigned char cc[4] = {c[u].x, c[u].y, c[u].z, c[u].w};
         float r[4];
 #pragma unroll
@@ -52,7 +76,8 @@ __global__ void __launch_bounds__(kStreamThreads) dequantize_kernel(
   // tail (and the whole tensor when the pointers are not 16-byte aligned)
   const unsigned first = vec_ok ? (groups << 2) : 0;
   for (unsigned e = first + blockIdx.x * kStreamThreads + threadIdx.x; e < n_elems; e += stride) {
-    const unsigned m = (e / n_frames) % n_mels;
+    const unsigned rowi = by_frames.div(e);
+    const unsigned m = rowi - by_mels.div(rowi) * n_mels;
     out[e] = __ldg(table + m * n_bins + min((unsigned)codes[e], kmax));
   }
 }
@@ -69,8 +94,9 @@ __device__ __forceinline__ unsigned char quantize_one(float x, float lo, float s
 
 __global__ void __launch_bounds__(kStreamThreads) quantize_kernel(
     const float* __restrict__ mel, uint8_t* __restrict__ codes, const float* __restrict__ lo,
-    const float* __restrict__ scale, unsigned n_elems, unsigned n_frames, unsigned n_mels,
+    const float* __restrict__ scale, unsigned n_elems, FastDiv by_frames, FastDiv by_mels,
     unsigned n_bins, bool vec_ok) {
+  const unsigned n_frames = by_frames.d, n_mels = by_mels.d;
   const unsigned groups = n_elems >> 2;
   const unsigned stride = gridDim.x * kStreamThreads;
   const float kmax = float(n_bins - 1);
@@ -87,9 +113,9 @@ __global__ void __launch_bounds__(kStreamThreads) quantize_kernel(
         const unsigned g = g0 + u * stride;
         if (g >= groups) continue;
         const unsigned e = g << 2;
-        unsigned rowi = e / n_frames;
+        const unsigned rowi = by_frames.div(e);
         unsigned t = e - rowi * n_frames;
-        unsigned m = rowi % n_mels;
+        unsigned m = rowi - by_mels.div(rowi) * n_mels;
         const float xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
         unsigned char r[4];
 #pragma unroll
@@ -103,7 +129,8 @@ __global__ void __launch_bounds__(kStreamThreads) quantize_kernel(
   }
   const unsigned first = vec_ok ? (groups << 2) : 0;
   for (unsigned e = first + blockIdx.x * kStreamThreads + threadIdx.x; e < n_elems; e += stride) {
-    const unsigned m = (e / n_frames) % n_mels;
+    const unsigned rowi = by_frames.div(e);
+    const unsigned m = rowi - by_mels.div(rowi) * n_mels;
     codes[e] = quantize_one(mel[e], __ldg(lo + m), __ldg(scale + m), kmax);
   }
 }

@@ -531,7 +531,7 @@ static int check_tensor(const void* a, const void* b, long long n_rows, int n_me
   if (n_rows < 0 || n_mels < 1 || n_frames < 1)
     return fail(DMEL_ERR_INVALID, "bad tensor shape (%lld, %d, %lld)", n_rows, n_mels, n_frames);
   const long long n = n_rows * (long long)n_mels * n_frames;
-  if (n >= (1LL << 32) - 4096) return fail(DMEL_ERR_INVALID, "tensor of %lld elements exceeds the 2^32 flat-index limit; split the batch", n);
+  if (n >= (1LL << 31)) return fail(DMEL_ERR_INVALID, "tensor of %lld elements exceeds the 2^31 flat-index limit; split the batch", n);
   *n_elems = (unsigned)n;
   return DMEL_OK;
 }
@@ -547,7 +547,7 @@ int dmel_quantize_u8(const float* logmel_dev, long long n_rows, int n_mels, long
   if (n == 0) return DMEL_OK;
   const bool vec = ((reinterpret_cast<uintptr_t>(logmel_dev) & 15) == 0) && ((reinterpret_cast<uintptr_t>(codes_dev) & 3) == 0);
   dmel::quantize_kernel<<<stream_grid(nullptr, n >> 2), dmel::kStreamThreads, 0, (cudaStream_t)stream>>>(
-      logmel_dev, codes_dev, lo_dev, scale_dev, n, (unsigned)n_frames, (unsigned)n_mels, (unsigned)n_bins, vec);
+      logmel_dev, codes_dev, lo_dev, scale_dev, n, dmel::FastDiv::make((unsigned)n_frames), dmel::FastDiv::make((unsigned)n_mels), (unsigned)n_bins, vec);
   DMEL_CUDA(cudaGetLastError());
   return DMEL_OK;
 }
@@ -562,7 +562,7 @@ int dmel_dequantize_f32(const uint8_t* codes_dev, long long n_rows, int n_mels, 
   if (n == 0) return DMEL_OK;
   const bool vec = ((reinterpret_cast<uintptr_t>(logmel_dev) & 15) == 0) && ((reinterpret_cast<uintptr_t>(codes_dev) & 3) == 0);
   dmel::dequantize_kernel<<<stream_grid(nullptr, n >> 2), dmel::kStreamThreads, 0, (cudaStream_t)stream>>>(
-      codes_dev, logmel_dev, table_dev, n, (unsigned)n_frames, (unsigned)n_mels, (unsigned)n_bins, vec);
+      codes_dev, logmel_dev, table_dev, n, dmel::FastDiv::make((unsigned)n_frames), dmel::FastDiv::make((unsigned)n_mels), (unsigned)n_bins, vec);
   DMEL_CUDA(cudaGetLastError());
   return DMEL_OK;
 }

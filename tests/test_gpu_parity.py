@@ -232,7 +232,8 @@ def test_quantizer_edge_cases(d):
     assert q.encode(torch.zeros(0, 3, 4, device="cuda")).shape == (0, 3, 4)
 
 
-@pytest.mark.parametrize("shape", [(1, 80, 1), (3, 80, 5), (2, 128, 937), (5, 100, 61), (1, 160, 5167)])
+@pytest.mark.parametrize("shape", [(1, 80, 1), (3, 80, 5), (2, 128, 937), (5, 100, 61), (1, 160, 5167), (1, 1, 5), (7, 3, 1),
+                                   (2, 64, 1024), (3, 1, 4097)])
 def test_streaming_kernels_odd_shapes(d, shape):
     """Flat-indexed quantise / dequantise / min-max cross row boundaries inside a 4-element group."""
     b, m, t = shape
