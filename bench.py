@@ -277,12 +277,115 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     }))
 
 
+# ---------------------------------------------------------------------------
+# secondary workloads (BASELINE configs[2], [3], [4]); not the headline line
+# ---------------------------------------------------------------------------
+def _init_rank():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    return rank, world, local_rank, torch.device("cuda", local_rank)
+
+
+def run_stream(args):
+    """configs[3]: one stream, 80 ms chunks, 16 kHz / 80 mel: per-chunk latency."""
+    import dmel_codec_b200 as d
+    from dmel_codec_b200 import synth
+    rank, world, local_rank, dev = _init_rank()
+    geom = dict(sample_rate=16000, n_fft=1024, win_length=1024, hop_length=256, n_mels=80)
+    tok = d.DMelTokenizer(n_bins=16, **geom).to(dev)
+    wav = synth.batch([0], 16000 * 30, 16000, "speech").to(dev)
+    tok.calibrate([wav])
+    enc = d.DMelStreamEncoder(tok, n_streams=1, capacity_samples=1 << 16)
+    chunk, lat = 1280, []
+    n_chunks = wav.shape[2] // chunk
+    for rep in range(3):  # first pass warms up
+        lat = []
+        for i in range(n_chunks):
+            x = wav[:, 0, i * chunk:(i + 1) * chunk]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            codes = enc.push(x)
+            torch.cuda.synchronize()
+            lat.append((time.perf_counter() - t0) * 1e6)
+        enc.flush()
+    lat.sort()
+    p50, p99 = lat[len(lat) // 2], lat[min(len(lat) - 1, int(len(lat) * 0.99))]
+    print(json.dumps({"metric": "dmel_stream_chunk_latency_us", "value": p50, "unit": "us (p50)", "p99_us": p99,
+                      "higher_is_better": False, "n_gpus": 1, "chunks": len(lat),
+                      "audio_seconds_per_second_one_stream": 0.08 / (sum(lat) / len(lat) * 1e-6),
+                      "config": {"workload": "configs[3]: batch 1, 80 ms chunks (1280 samples), 16 kHz, 80 mel, 16 bins; "
+                                             "chunk already on the device, latency = push() + stream sync; 5 frames per chunk",
+                                 "note": "launch-latency bound: 5.5 KB per call, byte roofline not meaningful"}}))
+
+
+def run_pool_workload(args, name):
+    """configs[2] (calibrate + encode of 10k utterances, sharded) and configs[4] (long-form 2048)."""
+    import torch.distributed as dist
+    import dmel_codec_b200 as d
+    from dmel_codec_b200 import distributed as D, synth
+    rank, world, local_rank, dev = _init_rank()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    if name == "calibrate":
+        geom = dict(sample_rate=16000, n_fft=1024, win_length=1024, hop_length=256, n_mels=80)
+        n_utts, seconds, n_bins, bsz, pool_n = 10000, 10, 16, 250, 500
+        label = "configs[2]: min/max calibration + encode of 10,000 x 10 s utterances (16 kHz, 80 mel, 16 bins), block-sharded"
+    else:
+        geom = dict(sample_rate=44100, n_fft=2048, win_length=2048, hop_length=512, n_mels=160)
+        n_utts, seconds, n_bins, bsz, pool_n = 32, 60, 32, 4, 4
+        label = "configs[4]: long-form 32 x 60 s, 44.1 kHz, n_fft 2048, hop 512, 160 mel, 32 bins, utterances sharded"
+    n = geom["sample_rate"] * seconds
+    tok = d.DMelTokenizer(n_bins=n_bins, **geom).to(dev)
+    mine = D.shard_range(n_utts, rank, world)
+    # a pool of distinct synthetic utterances stands in for the shard (content does not change the work)
+    pool = synth.device_batch(range(rank * pool_n, (rank + 1) * pool_n), n, geom["sample_rate"], dev)
+    def load(ids):
+        k = len(ids)
+        start = (ids[0] * 7) % max(1, pool_n - k + 1) if k <= pool_n else 0
+        return pool[start:start + k]
+    def job():
+        D.calibrate_sharded(tok, n_utts, load, bsz)            # pass 1 + the all-reduce
+        for _ in D.encode_sharded(tok, n_utts, load, bsz):     # pass 2
+            pass
+    job()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    job()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    if rank == 0:
+        audio_s = n_utts * seconds
+        bytes_alg = 2 * 4 * n_utts * n + n_utts * geom["n_mels"] * (n // geom["hop_length"])
+        peak, src = measured_peaks()
+        print(json.dumps({"metric": f"dmel_{name}_encode_audio_seconds_per_second", "value": audio_s / (ms.item() / 1e3),
+                          "unit": UNIT, "n_gpus": world, "ms_total": ms.item(), "higher_is_better": True,
+                          "scaling": "strong", "hbm_frac_all_gpus": bytes_alg / (ms.item() / 1e3) / 1e9 / (peak * world),
+                          "stats": {"lo_min": float(tok.quantizer.lo.min()), "hi_max": float(tok.quantizer.hi.max())},
+                          "config": {"workload": label, "launch": tok._plan(dev).describe(),
+                                     "data": f"pool of {pool_n} distinct synthetic utterances per rank, cycled"}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=["encode", "stream", "calibrate", "longform"], default="encode",
+                    help="encode = the headline configs[1] line; the others are secondary lines for DESIGN.md")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: leave out the CPU-baseline leg")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: leave out the host-buffer leg")
     args = ap.parse_args()
@@ -293,6 +396,10 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    if args.workload == "stream":
+        return run_stream(args)
+    if args.workload in ("calibrate", "longform"):
+        return run_pool_workload(args, args.workload)
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

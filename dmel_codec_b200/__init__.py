@@ -6,6 +6,7 @@ plus the dMel quantiser the reference's README describes but does not ship):
     LinearSpectrogram, LogMelSpectrogram      waveform -> log-mel
     DMelQuantizer, DMelResult                 log-mel <-> uint8 codes, calibration
     DMelTokenizer                             waveform -> codes (fused kernel)
+    DMelStreamEncoder                         the same, chunk by chunk (bit-identical to offline)
 
 Everything computes in hand-written sm_100a CUDA reached through the C ABI in
 ``include/dmel_b200.h``; importing the package is cheap, the first call loads
@@ -13,5 +14,7 @@ Everything computes in hand-written sm_100a CUDA reached through the C ABI in
 """
 from .spectrogram import LinearSpectrogram, LogMelSpectrogram
 from .quantizer import DMelQuantizer, DMelResult, DMelTokenizer
+from .streaming import DMelStreamEncoder
 
-__all__ = ["LinearSpectrogram", "LogMelSpectrogram", "DMelQuantizer", "DMelResult", "DMelTokenizer"]
+__all__ = ["LinearSpectrogram", "LogMelSpectrogram", "DMelQuantizer", "DMelResult", "DMelTokenizer",
+           "DMelStreamEncoder"]

@@ -30,6 +30,9 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p]),
     "dmel_encode_u8": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_void_p,
                                c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+    "dmel_encode_frames_u8": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_longlong,
+                                      c_longlong, c_longlong, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                      c_void_p]),
     "dmel_encode_host_u8": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_void_p,
                                     c_void_p, c_void_p, c_int, c_void_p]),
     "dmel_quantize_u8": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_int,

@@ -185,13 +185,16 @@ long long num_frames(const dmel_plan* plan, long long n_samples) {
   return 1 + (padded - plan->n_fft) / plan->hop;
 }
 
-// shared argument checks + parameter block for the three fused entry points
-int prepare_fused(dmel_plan* plan, const float* wav, long long n_rows, long long n_samples,
-                  long long row_stride, FusedParams* p, int* grid) {
+// shared argument checks + parameter block for the fused entry points.  The general form writes
+// frames [t_begin, t_begin + t_count) of rows whose samples [src_base, n_samples) are resident at
+// wav[row][0 ...]; offline calls use src_base = 0, t_begin = 0, t_count = T.
+int prepare_window(dmel_plan* plan, const float* wav, long long n_rows, long long n_samples, long long row_stride,
+                   long long src_base, long long t_begin, long long t_count, FusedParams* p, int* grid) {
   if (!plan) return fail(DMEL_ERR_INVALID, "plan is null");
   if (!wav) return fail(DMEL_ERR_INVALID, "waveform pointer is null");
-  if (n_rows < 0 || n_samples <= 0 || row_stride < n_samples)
-    return fail(DMEL_ERR_INVALID, "bad waveform shape: rows=%lld samples=%lld stride=%lld", n_rows, n_samples, row_stride);
+  if (n_rows < 0 || n_samples <= 0 || src_base < 0 || src_base >= n_samples || row_stride < n_samples - src_base)
+    return fail(DMEL_ERR_INVALID, "bad waveform shape: rows=%lld samples=%lld base=%lld stride=%lld", n_rows,
+                n_samples, src_base, row_stride);
   if (n_samples <= plan->pad_inner)
     return fail(DMEL_ERR_INVALID,
                 "reflect padding of %d needs more than %d samples per row, got %lld "
@@ -201,7 +204,18 @@ int prepare_fused(dmel_plan* plan, const float* wav, long long n_rows, long long
   if (n_samples > (1LL << 30)) return fail(DMEL_ERR_INVALID, "rows longer than 2^30 samples are not supported");
   const long long T = num_frames(plan, n_samples);
   if (T <= 0) return fail(DMEL_ERR_INVALID, "row of %lld samples is shorter than one frame", n_samples);
-  const long long tiles_per_row = (T + plan->tile_frames - 1) / plan->tile_frames;
+  if (t_count < 0) t_count = T - t_begin;
+  if (t_begin < 0 || t_count <= 0 || t_begin + t_count > T)
+    return fail(DMEL_ERR_INVALID, "frame window [%lld, %lld) outside the %lld frames of the row", t_begin,
+                t_begin + t_count, T);
+  if (src_base > 0) {
+    if (plan->pad_outer) return fail(DMEL_ERR_UNSUPPORTED, "windowed (streaming) calls do not support center=True");
+    const long long first_tap = t_begin * plan->hop - plan->pad_inner;
+    if (src_base > std::max<long long>(first_tap, 0))
+      return fail(DMEL_ERR_INVALID, "frame %lld needs sample %lld but the buffer starts at sample %lld", t_begin,
+                  std::max<long long>(first_tap, 0), src_base);
+  }
+  const long long tiles_per_row = (t_count + plan->tile_frames - 1) / plan->tile_frames;
   const long long n_tiles = tiles_per_row * n_rows;
   if (n_tiles > 0x7fffffffLL) return fail(DMEL_ERR_INVALID, "batch too large: %lld tiles", n_tiles);
   std::memset(p, 0, sizeof(*p));
@@ -209,7 +223,9 @@ int prepare_fused(dmel_plan* plan, const float* wav, long long n_rows, long long
   p->row_stride = row_stride;
   p->n_rows = (int)n_rows;
   p->n_samples = (int)n_samples;
-  p->n_frames = (int)T;
+  p->n_frames = (int)t_count;
+  p->t_begin = (int)t_begin;
+  p->src_base = (int)src_base;
   p->tiles_per_row = (int)tiles_per_row;
   p->n_tiles = (int)n_tiles;
   p->hop = plan->hop;
@@ -227,8 +243,13 @@ int prepare_fused(dmel_plan* plan, const float* wav, long long n_rows, long long
   p->n_bins = 1;
   p->kmax = 0.f;
   fill_offsets_for(plan->n_fft, plan->tile_frames, p);
-  *grid = (int)std::min<long long>(n_tiles, (long long)plan->sm_count * plan->ctas_per_sm);
+  *grid = (int)std::max<long long>(1, std::min<long long>(n_tiles, (long long)plan->sm_count * plan->ctas_per_sm));
   return DMEL_OK;
+}
+
+int prepare_fused(dmel_plan* plan, const float* wav, long long n_rows, long long n_samples,
+                  long long row_stride, FusedParams* p, int* grid) {
+  return prepare_window(plan, wav, n_rows, n_samples, row_stride, 0, 0, -1, p, grid);
 }
 
 int check_bins(int n_bins) {
@@ -441,6 +462,31 @@ int dmel_encode_u8(dmel_plan* plan, const float* wav_dev, long long n_rows, long
   p.logmel = logmel_dev;
   p.near_edge = near_edge_dev;
   p.edge_eps = edge_eps;
+  DeviceGuard guard(plan->device);
+  DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream));
+  return DMEL_OK;
+}
+
+int dmel_encode_frames_u8(dmel_plan* plan, const float* wav_dev, long long n_rows, long long row_stride,
+                          long long src_base, long long n_samples, long long t_begin, long long t_count,
+                          const float* lo_dev, const float* scale_dev, int n_bins, uint8_t* codes_dev,
+                          float* logmel_dev, void* stream) {
+  FusedParams p;
+  int grid = 0;
+  int rc = prepare_window(plan, wav_dev, n_rows, n_samples, row_stride, src_base, t_begin, t_count, &p, &grid);
+  if (rc != DMEL_OK) return rc;
+  if (!codes_dev && !logmel_dev) return fail(DMEL_ERR_INVALID, "codes_dev and logmel_dev are both null");
+  if (codes_dev) {
+    if ((rc = check_bins(n_bins)) != DMEL_OK) return rc;
+    if (!lo_dev || !scale_dev) return fail(DMEL_ERR_INVALID, "lo_dev / scale_dev is null");
+    p.q_lo = lo_dev;
+    p.q_scale = scale_dev;
+    p.n_bins = n_bins;
+    p.kmax = float(n_bins - 1);
+    p.codes = codes_dev;
+  }
+  if (n_rows == 0) return DMEL_OK;
+  p.logmel = logmel_dev;
   DeviceGuard guard(plan->device);
   DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream));
   return DMEL_OK;

@@ -38,8 +38,10 @@ struct FusedParams {
   const float* wav;         // (B, row_stride) device
   long long row_stride;     // samples between rows
   int n_rows;               // B
-  int n_samples;            // L
-  int n_frames;             // T
+  int n_samples;            // L: length of the (virtual) row the reflect padding refers to
+  int n_frames;             // frames written per row (T, or the window length when streaming)
+  int t_begin;              // absolute index of the first frame written (0 offline)
+  int src_base;             // virtual sample index of wav[row][0] (0 offline; > 0 when only a tail of the row is resident)
   int tiles_per_row;
   int n_tiles;
   int hop;
@@ -246,17 +248,18 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
     TileInfo ti;
     ti.row = tile / p.tiles_per_row;
     ti.t0 = (tile - ti.row * p.tiles_per_row) * TF;
-    ti.n_valid = p.n_frames;
+    ti.n_valid = p.n_frames;  // in frames of this launch's window
     if (p.lengths) {
-      const int nv = p.lengths[ti.row] / p.hop;
-      ti.n_valid = nv < p.n_frames ? nv : p.n_frames;
+      const int nv = p.lengths[ti.row] / p.hop - p.t_begin;
+      ti.n_valid = nv < 0 ? 0 : (nv < p.n_frames ? nv : p.n_frames);
     }
     // log-mel output covers every frame of the row; codes / statistics only the valid ones
     const int last = (kLogmel ? p.n_frames : ti.n_valid) - ti.t0;
     ti.frame_limit = last < 0 ? 0 : (last > TF ? TF : last);
-    const int s0 = ti.t0 * p.hop - p.pad_inner - p.pad_outer;
-    ti.async = row_vec_ok && s0 >= 0 && (s0 & 3) == 0 && s0 + p.wave_len <= p.n_samples;
-    ti.src0 = (long long)ti.row * p.row_stride + s0;
+    const int s0 = (p.t_begin + ti.t0) * p.hop - p.pad_inner - p.pad_outer;  // virtual sample under the tile's first tap
+    const int b0 = s0 - p.src_base;                                          // where that sample sits in the buffer
+    ti.async = row_vec_ok && s0 >= 0 && b0 >= 0 && (b0 & 3) == 0 && s0 + p.wave_len <= p.n_samples;
+    ti.src0 = (long long)ti.row * p.row_stride + b0;
     return ti;
   };
   // Start filling wave buffer b with the samples of a tile.
@@ -270,8 +273,8 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
         bulk_copy_g2s(wave, p.wav + ti.src0, p.wave_len * 4, &bars[b]);
       }
     } else {
-      const float* src = p.wav + (long long)ti.row * p.row_stride;
-      const int j0 = ti.t0 * p.hop;  // first position in the padded row
+      const float* src = p.wav + (long long)ti.row * p.row_stride - p.src_base;
+      const int j0 = (p.t_begin + ti.t0) * p.hop;  // first position in the padded row
       for (int i = tid; i < p.wave_len; i += kThreads) {
         const int j = j0 + i;
         float x = 0.f;

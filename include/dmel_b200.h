@@ -91,6 +91,20 @@ int dmel_encode_u8(dmel_plan* plan, const float* wav_dev, long long n_rows, long
                    uint8_t* codes_dev, float* logmel_dev,
                    unsigned long long* near_edge_dev, float edge_eps, void* stream);
 
+/* Windowed form for streaming: writes frames [t_begin, t_begin + t_count) only (t_count < 0 = to the
+ * end), for rows of which only samples [src_base, n_samples) are resident, at wav_dev[row][0 ...].
+ * n_samples is the row length the reflect padding refers to: while a stream is open pass the number
+ * of samples received so far and ask only for frames that end inside them; at end of stream pass the
+ * final length and the remaining frames get the reference's right-edge reflection.  The buffer must
+ * reach back to the first tap of frame t_begin (sample t_begin*hop - (n_fft-hop)/2, or 0).
+ * Output tensors are (n_rows, n_mels, t_count).  codes_dev or logmel_dev may be NULL (not both).
+ * The reference has no streaming mode; frame for frame the result equals dmel_encode_u8 on the
+ * whole row (reference utils/spectrogram.py:41-81 applied to the complete waveform). */
+int dmel_encode_frames_u8(dmel_plan* plan, const float* wav_dev, long long n_rows, long long row_stride,
+                          long long src_base, long long n_samples, long long t_begin, long long t_count,
+                          const float* lo_dev, const float* scale_dev, int n_bins,
+                          uint8_t* codes_dev, float* logmel_dev, void* stream);
+
 /* Same as dmel_encode_u8 with HOST buffers: chunks rows through pinned staging,
  * overlapping H2D, kernel and D2H on internal streams; returns when codes_host
  * is complete.  lengths_host may be NULL; lo/scale are host arrays too. */

@@ -284,3 +284,45 @@ def test_full_size_config2_properties(d):
     ok, ratio = logmel_close(mel[rows].cpu(), ref, REL_TOL)
     assert ok, f"{ratio:.2f}x tolerance"
     _check_codes(codes[rows], ref, tok.quantizer.lo.cpu(), tok.quantizer.hi.cpu(), 16)
+
+
+# ---------------------------------------------------------------------------
+# streaming (BASELINE configs[3]): chunked output == offline output, bit for bit
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("chunking", ["80ms", "ragged", "one_shot"])
+@pytest.mark.parametrize("n_streams", [1, 3])
+def test_streaming_equals_offline(d, chunking, n_streams):
+    from dmel_codec_b200 import synth
+    kw = GOLDEN_GEOMETRY["cfg1_16k_80"]
+    n = 16000 * 3 + 123
+    wav = synth.batch(range(700, 700 + n_streams), n, 16000, "speech").cuda()
+    tok = _tokenizer(d, kw, 16)
+    tok.calibrate([wav])
+    want, _ = tok.encode(wav)
+    enc = d.DMelStreamEncoder(tok, n_streams=n_streams, capacity_samples=8192)
+    if chunking == "80ms":
+        sizes = [1280] * (n // 1280) + ([n % 1280] if n % 1280 else [])
+    elif chunking == "ragged":
+        g = torch.Generator().manual_seed(3)
+        sizes, left = [], n
+        while left > 0:
+            c = min(left, int(torch.randint(1, 3000, (1,), generator=g)))
+            sizes.append(c)
+            left -= c
+    else:
+        enc = d.DMelStreamEncoder(tok, n_streams=n_streams, capacity_samples=n + 8)
+        sizes = [n]
+    parts, at, counts = [], 0, []
+    for c in sizes:
+        out = enc.push(wav[:, 0, at:at + c])
+        at += c
+        parts.append(out)
+        counts.append(out.shape[2])
+    parts.append(enc.flush())
+    got = torch.cat(parts, dim=2)
+    assert got.shape == want.shape and torch.equal(got, want)
+    if chunking == "80ms":
+        assert counts[0] == 3 and all(k == 5 for k in counts[1:-1])  # 3 frames, then 5 per chunk
+    # the encoder is reusable after flush()
+    again = torch.cat([enc.push(wav[:, 0, :4000]), enc.flush()], dim=2)
+    assert torch.equal(again, tok.encode(wav[:, :, :4000])[0])
