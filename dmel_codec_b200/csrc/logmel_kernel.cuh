@@ -2,11 +2,12 @@
 //
 // One CTA owns tiles of TF consecutive frames of one utterance row:
 //   1. the (TF-1)*hop + n_fft samples of the NEXT tile are pulled into shared
-//      memory by one bulk async copy (cp.async.bulk + mbarrier, double
-//      buffered) while the current tile computes; row ends, where the
-//      reference reflect-pads (utils/spectrogram.py:58-62), are staged by
-//      ordinary reflect-indexed loads.  The 4x frame overlap is re-read on
-//      chip, never from HBM;
+//      memory by one bulk async copy (cp.async.bulk + mbarrier) as soon as the
+//      FFTs of the current tile have consumed the buffer, i.e. the copy flies
+//      under the mel/epilogue phase (and under the other CTA of the SM); row
+//      ends, where the reference reflect-pads (utils/spectrogram.py:58-62),
+//      are staged by ordinary reflect-indexed loads.  The 4x frame overlap is
+//      re-read on chip, never from HBM;
 //   2. each warp turns frames into magnitudes with the register FFT of
 //      fft_core.cuh (window multiply on load, torch.stft at :64-75, magnitude
 //      at :76) and drops them in a [frame][bin] shared tile;
@@ -137,10 +138,8 @@ struct FusedLayout {
   static __host__ __device__ size_t tiles_off() { return 0; }
   static __host__ __device__ size_t mags_off() { return size_t(kWarps) * kTileF2 * sizeof(float2); }
   static __host__ __device__ size_t wave_off() { return align16(mags_off() + size_t(kMagFloats) * 4); }
-  static __host__ __device__ size_t window_off(int wave_len) { return align16(wave_off() + 2 * size_t(wave_len) * 4); }
-  static __host__ __device__ size_t fold_off(int wave_len) {
-    return align16(window_off(wave_len) + (NFFT == 2048 ? size_t(NFFT) * 4 : 0));
-  }
+  static __host__ __device__ size_t window_off(int wave_len) { return align16(wave_off() + size_t(wave_len) * 4); }
+  static __host__ __device__ size_t fold_off(int wave_len) { return align16(window_off(wave_len) + size_t(NFFT) * 4); }
   static __host__ __device__ size_t chan_off(int wave_len) {
     return align16(fold_off(wave_len) + (NFFT == 2048 ? size_t(kFoldN) * 8 : 0));
   }
@@ -212,8 +211,8 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
   }
   for (int i = tid; i < p.nnz; i += kThreads) s_weights[i] = p.weights[i];
   for (int i = tid; i < LY::kMagFloats; i += kThreads) mags[i] = 0.f;  // the 3 pad columns of each row stay zero
+  for (int i = tid; i < NFFT; i += kThreads) s_window[i] = p.window[i];
   if constexpr (NFFT == 2048) {
-    for (int i = tid; i < NFFT; i += kThreads) s_window[i] = p.window[i];
     for (int i = tid; i < LY::kFoldN; i += kThreads) s_fold[i] = p.fold_tw[i];
   }
   if (tid == 0) {
@@ -227,22 +226,17 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
   float2 tw[kPts];                              // inter-pass twiddles W_{NFFT/2}^{lane*k1}
 #pragma unroll
   for (int k1 = 0; k1 < kPts; ++k1) tw[k1] = p.stage_tw[k1 * 32 + lane];
-  float2 win[NFFT == 1024 ? 16 : 1];            // window taps of this lane's samples
   float2 fold_base = make_float2(1.f, 0.f);     // W_1024^lane
-  if constexpr (NFFT == 1024) {
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-      const int idx = 2 * (32 * n1 + lane);
-      win[n1] = make_float2(p.window[idx], p.window[idx + 1]);
-    }
-    fold_base = p.fold_tw[lane];
-  }
+  if constexpr (NFFT == 1024) fold_base = p.fold_tw[lane];
+  // the window taps of this lane's samples are re-read from shared memory for every frame: keeping
+  // them in 32 registers starved the scheduler of temporaries under the 128-register cap
+  const float2* my_win = reinterpret_cast<const float2*>(s_window) + lane;
 
   const int padded_len = p.n_samples + 2 * p.pad_inner + 2 * p.pad_outer;
   const bool hop_even = (p.hop & 1) == 0;
   const bool row_vec_ok = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0) && ((p.row_stride & 3) == 0);
   unsigned long long edge_hits = 0;
-  uint32_t phase_bits = 0;  // bit b: parity to wait for on bars[b]
+  uint32_t phase_bits = 0;  // parity to wait for on the staging barrier
 
   auto describe = [&](int tile) {
     TileInfo ti;
@@ -262,15 +256,15 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
     ti.src0 = (long long)ti.row * p.row_stride + b0;
     return ti;
   };
-  // Start filling wave buffer b with the samples of a tile.
-  auto stage = [&](const TileInfo& ti, int b) {
+  // Start filling the wave buffer with the samples of a tile (the buffer must be free).
+  auto stage = [&](const TileInfo& ti) {
     if (ti.frame_limit == 0) return;
-    float* wave = wave0 + b * p.wave_len;
+    float* wave = wave0;
     if (ti.async) {
       if (tid == 0) {
         fence_proxy_async();  // earlier generic-proxy reads of this buffer are ordered before the async write
-        mbar_expect_tx(&bars[b], p.wave_len * 4);
-        bulk_copy_g2s(wave, p.wav + ti.src0, p.wave_len * 4, &bars[b]);
+        mbar_expect_tx(&bars[0], p.wave_len * 4);
+        bulk_copy_g2s(wave, p.wav + ti.src0, p.wave_len * 4, &bars[0]);
       }
     } else {
       const float* src = p.wav + (long long)ti.row * p.row_stride - p.src_base;
@@ -287,25 +281,23 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
   __syncthreads();  // constants + barrier init visible
   int tile = blockIdx.x;
   TileInfo cur = describe(tile < p.n_tiles ? tile : 0);
-  if (tile < p.n_tiles) stage(cur, 0);
+  if (tile < p.n_tiles) stage(cur);
 
-  for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
-    const int b = it & 1;
-    const float* wave = wave0 + b * p.wave_len;
+  for (; tile < p.n_tiles; tile += gridDim.x) {
+    const float* wave = wave0;
     const bool dead = cur.frame_limit == 0;
 
-    // ---- 1. this tile's samples are in wave[b]; start fetching the next tile
+    // ---- 1. wait for this tile's samples
     if (!dead) {
       if (cur.async) {
-        mbar_wait(&bars[b], (phase_bits >> b) & 1u);
-        phase_bits ^= 1u << b;
+        mbar_wait(&bars[0], phase_bits & 1u);
+        phase_bits ^= 1u;
       } else {
         __syncthreads();  // plain stores of all threads
       }
     }
     const bool has_next = tile + (int)gridDim.x < p.n_tiles;
     const TileInfo nxt = describe(has_next ? tile + (int)gridDim.x : tile);
-    if (has_next) stage(nxt, b ^ 1);
 
     // ---- 2. FFT -> magnitudes ------------------------------------------------
     if constexpr (NFFT == 1024) {
@@ -318,15 +310,12 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
         if (hop_even) {
           const float2* f2 = reinterpret_cast<const float2*>(fa);
 #pragma unroll
-          for (int n1 = 0; n1 < 16; ++n1) {
-            const float2 x = f2[32 * n1 + lane];
-            v[n1] = make_float2(x.x * win[n1].x, x.y * win[n1].y);
-          }
+          for (int n1 = 0; n1 < 16; ++n1) v[n1] = f2_mul(f2[32 * n1 + lane], my_win[32 * n1]);
         } else {
 #pragma unroll
           for (int n1 = 0; n1 < 16; ++n1) {
             const int idx = 2 * (32 * n1 + lane);
-            v[n1] = make_float2(fa[idx] * win[n1].x, fa[idx + 1] * win[n1].y);
+            v[n1] = f2_mul(make_float2(fa[idx], fa[idx + 1]), my_win[32 * n1]);
           }
         }
         __syncwarp();  // previous frame's pass-2 reads of my_tile are done
@@ -353,8 +342,7 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
 #pragma unroll
         for (int n1 = 0; n1 < 32; ++n1) {
           const int idx = 2 * (32 * n1 + lane);
-          const float2 w = *reinterpret_cast<const float2*>(s_window + idx);
-          v[n1] = make_float2(fa[idx] * w.x, fa[idx + 1] * w.y);
+          v[n1] = f2_mul(make_float2(fa[idx], fa[idx + 1]), my_win[32 * n1]);
         }
         __syncwarp();
         fft1024_pass1(v, tw, my_tile, lane);
@@ -382,6 +370,8 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
       }
     }
     __syncthreads();
+    // the wave buffer is free: fetch the next tile under the mel phase
+    if (has_next) stage(nxt);
 
     // ---- 3. mel filterbank, log, quantise --------------------------------
     // One lane per frame, 32/TF adjacent channels side by side in a warp.  The host pads the spans
@@ -418,15 +408,21 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
           const float4* x4 = reinterpret_cast<const float4*>(mrow + (c.x & 0xffff));
           const float4* x4_end = x4 + (c.x >> 18);  // span length / 4: >= 1, identical across the warp
           float acc = 0.f;
+          float4 w = *w4++, x = *x4++;  // the loads of the next four bins are in flight during the FMAs
 #pragma unroll 1
-          do {
-            const float4 w = *w4++;
-            const float4 x = *x4++;
+          while (x4 != x4_end) {
+            const float4 wn = *w4++, xn = *x4++;
             acc = fmaf(w.x, x.x, acc);
             acc = fmaf(w.y, x.y, acc);
             acc = fmaf(w.z, x.z, acc);
             acc = fmaf(w.w, x.w, acc);
-          } while (x4 != x4_end);
+            w = wn;
+            x = xn;
+          }
+          acc = fmaf(w.x, x.x, acc);
+          acc = fmaf(w.y, x.y, acc);
+          acc = fmaf(w.z, x.z, acc);
+          acc = fmaf(w.w, x.w, acc);
           const float value = fast_log(fmaxf(acc, kLogClip));
           if constexpr (kLogmel) {
             if (live && in_row) p.logmel[o] = value;
@@ -457,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
         }
       }
     }
-    __syncthreads();  // mags and wave[b] are free again
+    __syncthreads();  // mags are free again; plain-store staging of the next tile is visible
     cur = nxt;
   }
 
