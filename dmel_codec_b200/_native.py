@@ -12,7 +12,7 @@ from ctypes import (POINTER, c_char_p, c_float, c_int, c_int32, c_longlong, c_ui
                     c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdmel_b200.so")
+LIB_PATH = os.environ.get("DMEL_LIB") or os.path.join(_HERE, "libdmel_b200.so")  # DMEL_LIB: A/B builds
 
 ABI_VERSION = 1
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = -1, -2, -3, -4

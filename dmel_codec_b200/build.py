@@ -18,7 +18,7 @@ OUT = os.path.join(HERE, "libdmel_b200.so")
 SOURCES = ["dmel_b200.cu"]
 DEPS = ["dmel_b200.cu", "logmel_kernel.cuh", "fft_core.cuh", "codec_kernels.cuh",
         os.path.join("..", "..", "include", "dmel_b200.h")]
-NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+NVCC_FLAGS = ["-std=c++20", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 
 
@@ -39,7 +39,8 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return OUT
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", OUT, *[os.path.join(CSRC, s) for s in SOURCES]]
+    extra = os.environ.get("DMEL_NVCC_EXTRA", "").split()  # e.g. -DDMEL_SCALAR_FP for A/B measurements
+    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-o", OUT, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

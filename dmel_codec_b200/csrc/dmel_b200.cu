@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -79,49 +80,68 @@ namespace {
 
 using dmel::FusedParams;
 
-template <int NFFT, int TF>
-size_t fused_smem(int wave_len, int n_mels, int nnz) {
-  return dmel::FusedLayout<NFFT, TF>::total(wave_len, n_mels, nnz);
+// The kernel variants this build carries: (n_fft, frames per tile, CTAs per SM).
+struct Variant {
+  int n_fft, tf, occ;
+};
+constexpr Variant kVariants[] = {{1024, 8, 3}, {1024, 16, 2}, {1024, 8, 2}, {1024, 16, 1}, {1024, 8, 1},
+                                 {2048, 16, 1}, {2048, 8, 1}};
+
+// calls f.template operator()<NFFT, TF, OCC>() for the variant (compile-time dispatch)
+template <typename F>
+auto dispatch_variant(int n_fft, int tf, int occ, F&& f) {
+  if (n_fft == 1024) {
+    if (tf == 8 && occ == 3) return f.template operator()<1024, 8, 3>();
+    if (tf == 16) return occ == 2 ? f.template operator()<1024, 16, 2>() : f.template operator()<1024, 16, 1>();
+    return occ == 2 ? f.template operator()<1024, 8, 2>() : f.template operator()<1024, 8, 1>();
+  }
+  return tf == 16 ? f.template operator()<2048, 16, 1>() : f.template operator()<2048, 8, 1>();
 }
 
-template <int NFFT, int TF>
-void fill_offsets(FusedParams* p) {
-  using LY = dmel::FusedLayout<NFFT, TF>;
-  p->off_mags = (int)LY::mags_off();
-  p->off_wave = (int)LY::wave_off();
-  p->off_window = (int)LY::window_off(p->wave_len);
-  p->off_fold = (int)LY::fold_off(p->wave_len);
-  p->off_chan = (int)LY::chan_off(p->wave_len);
-  p->off_weights = (int)LY::weights_off(p->wave_len, p->n_chan_pad);
-  p->off_perchan = (int)LY::perchan_off(p->wave_len, p->n_chan_pad, p->nnz);
-  p->off_bars = (int)LY::bar_off(p->wave_len, p->n_chan_pad, p->nnz);
-}
+struct FillOffsets {
+  FusedParams* p;
+  template <int NFFT, int TF, int OCC>
+  int operator()() const {
+    using LY = dmel::FusedLayout<NFFT, TF, OCC>;
+    p->off_mags = (int)LY::mags_off();
+    p->off_wave = (int)LY::wave_off();
+    p->off_window = (int)LY::window_off(p->wave_len);
+    p->off_fold = (int)LY::fold_off(p->wave_len);
+    p->off_chan = (int)LY::chan_off(p->wave_len);
+    p->off_weights = (int)LY::weights_off(p->wave_len, p->n_chan_pad);
+    p->off_perchan = (int)LY::perchan_off(p->wave_len, p->n_chan_pad, p->nnz);
+    p->off_bars = (int)LY::bar_off(p->wave_len, p->n_chan_pad, p->nnz);
+    return 0;
+  }
+};
 
-void fill_offsets_for(int n_fft, int tf, FusedParams* p) {
-  if (n_fft == 1024) return tf == 16 ? fill_offsets<1024, 16>(p) : fill_offsets<1024, 8>(p);
-  return tf == 16 ? fill_offsets<2048, 16>(p) : fill_offsets<2048, 8>(p);
-}
+struct SmemNeed {
+  int wave_len, n_chan, nnz;
+  template <int NFFT, int TF, int OCC>
+  size_t operator()() const {
+    return dmel::FusedLayout<NFFT, TF, OCC>::total(wave_len, n_chan, nnz);
+  }
+};
 
-size_t fused_smem_for(int n_fft, int tf, int wave_len, int n_mels, int nnz) {
-  if (n_fft == 1024) return tf == 16 ? fused_smem<1024, 16>(wave_len, n_mels, nnz) : fused_smem<1024, 8>(wave_len, n_mels, nnz);
-  return tf == 16 ? fused_smem<2048, 16>(wave_len, n_mels, nnz) : fused_smem<2048, 8>(wave_len, n_mels, nnz);
-}
-
-template <int NFFT, int TF, int MODE>
-cudaError_t launch_fused(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st) {
-  auto kern = dmel::dmel_fused_kernel<NFFT, TF, MODE>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
-  if (e != cudaSuccess) return e;
-  kern<<<grid, dmel::kThreads, plan->smem_bytes, st>>>(p);
-  return cudaGetLastError();
-}
+template <int MODE>
+struct Launch {
+  const dmel_plan* plan;
+  const FusedParams* p;
+  int grid;
+  cudaStream_t st;
+  template <int NFFT, int TF, int OCC>
+  cudaError_t operator()() const {
+    auto kern = dmel::dmel_fused_kernel<NFFT, TF, MODE, OCC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, dmel::kThreads, plan->smem_bytes, st>>>(*p);
+    return cudaGetLastError();
+  }
+};
 
 template <int MODE>
 cudaError_t launch_fused_mode(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st) {
-  const int tf = plan->tile_frames;
-  if (plan->n_fft == 1024)
-    return tf == 16 ? launch_fused<1024, 16, MODE>(plan, p, grid, st) : launch_fused<1024, 8, MODE>(plan, p, grid, st);
-  return tf == 16 ? launch_fused<2048, 16, MODE>(plan, p, grid, st) : launch_fused<2048, 8, MODE>(plan, p, grid, st);
+  return dispatch_variant(plan->n_fft, plan->tile_frames, plan->ctas_per_sm, Launch<MODE>{plan, &p, grid, st});
 }
 
 cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st) {
@@ -242,7 +262,8 @@ int prepare_window(dmel_plan* plan, const float* wav, long long n_rows, long lon
   p->weights = plan->d_weights;
   p->n_bins = 1;
   p->kmax = 0.f;
-  fill_offsets_for(plan->n_fft, plan->tile_frames, p);
+  if (const char* dbg = std::getenv("DMEL_DEBUG_SKIP")) p->debug_skip = std::atoi(dbg);  // ablation timing only
+  dispatch_variant(plan->n_fft, plan->tile_frames, plan->ctas_per_sm, FillOffsets{p});
   *grid = (int)std::max<long long>(1, std::min<long long>(n_tiles, (long long)plan->sm_count * plan->ctas_per_sm));
   return DMEL_OK;
 }
@@ -319,30 +340,30 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
       return fail(DMEL_ERR_INVALID, "mel_basis[%zu] is not finite", i);
     }
 
-  // frame tile: prefer one that lets two CTAs share an SM (n_fft 1024 kernels are built for
-  // 128 registers / 2 CTAs), else the largest that fits at all
+  // pick the first kernel variant (most CTAs per SM first) whose shared memory fits; DMEL_OCC=<n>
+  // pins the CTAs-per-SM choice (experiments)
   int max_sm_smem = 0;
   DMEL_CUDA(cudaDeviceGetAttribute(&max_sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, plan->device));
-  const size_t half_sm = (size_t)max_sm_smem / 2 - 1024;  // 1 KB per CTA is reserved by the driver
-  const int candidates[2] = {16, 8};
+  const char* occ_env = std::getenv("DMEL_OCC");
+  const int occ_pin = occ_env ? std::atoi(occ_env) : 0;
   std::vector<int2> chan;
   std::vector<float> weights;
-  for (int pass = 0; pass < 2 && !plan->tile_frames; ++pass)
-    for (int tf : candidates) {
-      band_filterbank(mel_basis_host, n_mels, n_fft / 2 + 1, 32 / tf, &chan, &weights);
-      const int wave_len = ((tf - 1) * hop_length + n_fft + 3) / 4 * 4;
-      const size_t need = fused_smem_for(n_fft, tf, wave_len, (int)chan.size(), (int)weights.size());
-      const size_t limit = (pass == 0 && n_fft == 1024) ? half_sm : (size_t)plan->max_smem;
-      if (need <= limit) {
-        plan->tile_frames = tf;
-        plan->wave_len = wave_len;
-        plan->smem_bytes = need;
-        plan->ctas_per_sm = (n_fft == 1024 && need <= half_sm) ? 2 : 1;
-        plan->nnz = (int)weights.size();
-        plan->n_chan_pad = (int)chan.size();
-        break;
-      }
+  for (const Variant& v : kVariants) {
+    if (v.n_fft != n_fft || (occ_pin && v.occ != occ_pin)) continue;
+    band_filterbank(mel_basis_host, n_mels, n_fft / 2 + 1, 32 / v.tf, &chan, &weights);
+    const int wave_len = ((v.tf - 1) * hop_length + n_fft + 3) / 4 * 4;
+    const size_t need = dispatch_variant(v.n_fft, v.tf, v.occ, SmemNeed{wave_len, (int)chan.size(), (int)weights.size()});
+    const size_t limit = std::min<size_t>((size_t)max_sm_smem / v.occ - 1024, (size_t)plan->max_smem);  // 1 KB/CTA reserved
+    if (need <= limit) {
+      plan->tile_frames = v.tf;
+      plan->wave_len = wave_len;
+      plan->smem_bytes = need;
+      plan->ctas_per_sm = v.occ;
+      plan->nnz = (int)weights.size();
+      plan->n_chan_pad = (int)chan.size();
+      break;
     }
+  }
   if (!plan->tile_frames) {
     const int max_smem = plan->max_smem;
     delete plan;
@@ -515,9 +536,12 @@ int dmel_encode_host_u8(dmel_plan* plan, const float* wav_host, long long n_rows
     DMEL_CUDA(cudaMalloc((void**)&plan->d_lo, plan->n_mels * sizeof(float)));
     DMEL_CUDA(cudaMalloc((void**)&plan->d_scale, plan->n_mels * sizeof(float)));
   }
-  // rows per chunk: about 16 MiB of waveform, so copies and kernels of neighbouring chunks overlap
+  // rows per chunk: a few MiB of waveform (DMEL_HOST_CHUNK_MB, default 4), so copies and kernels of
+  // neighbouring chunks overlap and the un-overlapped tail (last kernel + last D2H) stays short
   const long long row_bytes = n_samples * 4;
-  long long chunk_rows = std::max<long long>(1, (16LL << 20) / row_bytes);
+  long long chunk_mb = 4;
+  if (const char* env = std::getenv("DMEL_HOST_CHUNK_MB")) chunk_mb = std::max(1, std::atoi(env));
+  long long chunk_rows = std::max<long long>(1, (chunk_mb << 20) / row_bytes);
   chunk_rows = std::min(chunk_rows, n_rows);
   const size_t wav_need = (size_t)chunk_rows * n_samples;
   const size_t codes_need = (size_t)chunk_rows * plan->n_mels * T;

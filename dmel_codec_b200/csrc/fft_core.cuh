@@ -51,14 +51,19 @@ DMEL_HD constexpr float cos32_q(int q) {
 DMEL_HD constexpr float cos32(int q) { return q <= 8 ? cos32_q(q) : -cos32_q(16 - q); }
 DMEL_HD constexpr float sin32(int q) { return q <= 8 ? cos32_q(8 - q) : cos32_q(q - 8); }
 
-// ---- packed fp32x2 arithmetic -------------------------------------------------
-// sm_100 executes add/mul/fma on an aligned register PAIR in one instruction (PTX
-// add/mul/fma.rn.f32x2, SASS FADD2/FMUL2/FFMA2) and takes operand swizzles (swap halves,
-// negate one half, broadcast a scalar) for free.  A complex number is such a pair, so every
-// complex add is one instruction and every complex multiply two.  The kernel is bound by
-// instruction issue, not by the FMA pipe, which makes this the cheapest 2x on the FFT.
-// The host versions spell out the same operations in the same order for tests/host_emul.cu.
-#ifdef __CUDA_ARCH__
+// ---- complex arithmetic on (re, im) pairs ---------------------------------------
+// sm_100 can execute add/mul/fma on an aligned register PAIR in one instruction (PTX
+// add/mul/fma.rn.f32x2, SASS FADD2/FMUL2/FFMA2) with free operand swizzles (swap halves, negate
+// one half, broadcast a scalar): a complex add is one instruction, a complex multiply two.
+// Build with -DDMEL_PACKED_F32X2 to use them.  Measured on B200 (profiles/history.md): warp
+// instructions per frame drop 1295 -> 1096, but a packed op holds the FMA pipe for two issue
+// cycles and IPC falls by the same factor; the scalar build is 1.5-2 % faster in every
+// configuration tried, so scalar FADD/FMUL/FFMA is the default.  Either way the host versions
+// spell out the same operations in the same order for tests/host_emul.cu.
+#if !defined(__CUDA_ARCH__)
+#undef DMEL_PACKED_F32X2
+#endif
+#ifdef DMEL_PACKED_F32X2
 __device__ __forceinline__ unsigned long long f2_pack(float2 a) {
   unsigned long long r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
@@ -71,7 +76,7 @@ __device__ __forceinline__ float2 f2_unpack(unsigned long long r) {
 }
 #endif
 DMEL_HD float2 f2_add(float2 a, float2 b) {
-#ifdef __CUDA_ARCH__
+#ifdef DMEL_PACKED_F32X2
   unsigned long long d;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
   return f2_unpack(d);
@@ -80,7 +85,7 @@ DMEL_HD float2 f2_add(float2 a, float2 b) {
 #endif
 }
 DMEL_HD float2 f2_mul(float2 a, float2 b) {
-#ifdef __CUDA_ARCH__
+#ifdef DMEL_PACKED_F32X2
   unsigned long long d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
   return f2_unpack(d);
@@ -89,7 +94,7 @@ DMEL_HD float2 f2_mul(float2 a, float2 b) {
 #endif
 }
 DMEL_HD float2 f2_fma(float2 a, float2 b, float2 c) {
-#ifdef __CUDA_ARCH__
+#ifdef DMEL_PACKED_F32X2
   unsigned long long d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
   return f2_unpack(d);
@@ -219,6 +224,33 @@ DMEL_HD void fft512_pass1(float2 (&v)[16], const float2 (&tw)[16], float2* tile,
     const float2 y = v[brev4(k1)];
     tile[k1 * kTilePitch + col] = (k1 == 0) ? y : cmul(y, tw[k1]);
   }
+}
+
+// Same pass with the 15 twiddles rebuilt per frame from four of them (w1, w2, w4, w8 =
+// W_512^{n2*{1,2,4,8}}): 11 extra complex multiplies buy back 22 registers, which is what lets a
+// third CTA fit on the SM.
+DMEL_HD void fft512_pass1_pow(float2 (&v)[16], float2 w1, float2 w2, float2 w4, float2 w8, float2* tile, int lane) {
+  radix16(v);
+  const int odd = lane & 1;
+  float2* col = tile + odd * 16 + (((lane >> 1) + 8 * odd) & 15);
+  const float2 w3 = cmul(w1, w2);
+  col[0 * kTilePitch] = v[brev4(0)];
+  col[8 * kTilePitch] = cmul(v[brev4(8)], w8);
+  col[1 * kTilePitch] = cmul(v[brev4(1)], w1);
+  col[9 * kTilePitch] = cmul(cmul(v[brev4(9)], w1), w8);
+  col[2 * kTilePitch] = cmul(v[brev4(2)], w2);
+  col[10 * kTilePitch] = cmul(cmul(v[brev4(10)], w2), w8);
+  col[3 * kTilePitch] = cmul(v[brev4(3)], w3);
+  col[11 * kTilePitch] = cmul(cmul(v[brev4(11)], w3), w8);
+  col[4 * kTilePitch] = cmul(v[brev4(4)], w4);
+  col[12 * kTilePitch] = cmul(cmul(v[brev4(12)], w4), w8);
+  const float2 w5 = cmul(w4, w1), w6 = cmul(w4, w2), w7 = cmul(w4, w3);
+  col[5 * kTilePitch] = cmul(v[brev4(5)], w5);
+  col[13 * kTilePitch] = cmul(cmul(v[brev4(13)], w5), w8);
+  col[6 * kTilePitch] = cmul(v[brev4(6)], w6);
+  col[14 * kTilePitch] = cmul(cmul(v[brev4(14)], w6), w8);
+  col[7 * kTilePitch] = cmul(v[brev4(7)], w7);
+  col[15 * kTilePitch] = cmul(cmul(v[brev4(15)], w7), w8);
 }
 
 // Pass 2, lane = k1 + 16*h: radix-16 over the n2 of parity h of row k1.

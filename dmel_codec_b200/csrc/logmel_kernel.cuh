@@ -2,12 +2,11 @@
 //
 // One CTA owns tiles of TF consecutive frames of one utterance row:
 //   1. the (TF-1)*hop + n_fft samples of the NEXT tile are pulled into shared
-//      memory by one bulk async copy (cp.async.bulk + mbarrier) as soon as the
-//      FFTs of the current tile have consumed the buffer, i.e. the copy flies
-//      under the mel/epilogue phase (and under the other CTA of the SM); row
-//      ends, where the reference reflect-pads (utils/spectrogram.py:58-62),
-//      are staged by ordinary reflect-indexed loads.  The 4x frame overlap is
-//      re-read on chip, never from HBM;
+//      memory by one bulk async copy (cp.async.bulk + mbarrier, double
+//      buffered) while the current tile computes; row ends, where the
+//      reference reflect-pads (utils/spectrogram.py:58-62), are staged by
+//      ordinary reflect-indexed loads.  The 4x frame overlap is re-read on
+//      chip, never from HBM;
 //   2. each warp turns frames into magnitudes with the register FFT of
 //      fft_core.cuh (window multiply on load, torch.stft at :64-75, magnitude
 //      at :76) and drops them in a [frame][bin] shared tile;
@@ -67,6 +66,7 @@ struct FusedParams {
   // byte offsets of the shared-memory regions (FusedLayout, filled in by the host so the kernel
   // does no layout arithmetic)
   int off_mags, off_wave, off_window, off_fold, off_chan, off_weights, off_perchan, off_bars;
+  int debug_skip;           // diagnostics (env DMEL_DEBUG_SKIP): 1 skip the FFT phase, 2 skip mel/epilogue, 4 skip staging
   float* run_min;           // (M) running min, updated in place [kOutStats]
   float* run_max;           // (M)
   unsigned long long* near_edge;  // [kOutEdge]
@@ -123,8 +123,13 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
                : "memory");
 }
 
-template <int NFFT, int TF>
+// OCC = CTAs per SM the instantiation is built for.  OCC == 3 (n_fft 1024, TF 8 only) trades
+// registers and shared memory for a third CTA: window taps and twiddles are not kept in
+// registers (85-register budget) and the waveform tile is single-buffered.
+template <int NFFT, int TF, int OCC>
 struct FusedLayout {
+  static constexpr int kWaveBufs = OCC == 3 ? 1 : 2;
+  static constexpr bool kWindowInSmem = NFFT == 2048 || OCC == 3;
   static constexpr int kBins = NFFT / 2 + 1;
   // row pitch 516 / 1028 floats: a multiple of 4 so a lane can fetch four bins of its frame with
   // one LDS.128, and == 4 (mod 32) so the eight lanes of a quarter-warp (eight frames) cover all
@@ -138,8 +143,10 @@ struct FusedLayout {
   static __host__ __device__ size_t tiles_off() { return 0; }
   static __host__ __device__ size_t mags_off() { return size_t(kWarps) * kTileF2 * sizeof(float2); }
   static __host__ __device__ size_t wave_off() { return align16(mags_off() + size_t(kMagFloats) * 4); }
-  static __host__ __device__ size_t window_off(int wave_len) { return align16(wave_off() + size_t(wave_len) * 4); }
-  static __host__ __device__ size_t fold_off(int wave_len) { return align16(window_off(wave_len) + size_t(NFFT) * 4); }
+  static __host__ __device__ size_t window_off(int wave_len) { return align16(wave_off() + kWaveBufs * size_t(wave_len) * 4); }
+  static __host__ __device__ size_t fold_off(int wave_len) {
+    return align16(window_off(wave_len) + (kWindowInSmem ? size_t(NFFT) * 4 : 0));
+  }
   static __host__ __device__ size_t chan_off(int wave_len) {
     return align16(fold_off(wave_len) + (NFFT == 2048 ? size_t(kFoldN) * 8 : 0));
   }
@@ -166,11 +173,13 @@ struct TileInfo {
   long long src0;   // sample offset of padded-row position t0*hop in the flat waveform, if interior
 };
 
-template <int NFFT, int TF, int MODE>
-__global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_kernel(const FusedParams p) {
+template <int NFFT, int TF, int MODE, int OCC>
+__global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedParams p) {
+  static_assert(OCC == 1 || OCC == 2 || (OCC == 3 && NFFT == 1024 && TF == 8), "occupancy variants");
   static_assert(NFFT == 1024 || NFFT == 2048, "register FFT cores: 512 and 1024 complex points");
   static_assert(TF == 32 || TF == 16 || TF == 8, "tile frames");
-  using LY = FusedLayout<NFFT, TF>;
+  using LY = FusedLayout<NFFT, TF, OCC>;
+  constexpr bool kLean = OCC == 3;  // register-lean variant
   constexpr int kPitch = LY::kMagPitch;
   constexpr bool kCodes = (MODE & kOutCodes) != 0, kLogmel = (MODE & kOutLogmel) != 0;
   constexpr bool kStats = (MODE & kOutStats) != 0, kEdge = (MODE & kOutEdge) != 0;
@@ -211,7 +220,9 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
   }
   for (int i = tid; i < p.nnz; i += kThreads) s_weights[i] = p.weights[i];
   for (int i = tid; i < LY::kMagFloats; i += kThreads) mags[i] = 0.f;  // the 3 pad columns of each row stay zero
-  for (int i = tid; i < NFFT; i += kThreads) s_window[i] = p.window[i];
+  if constexpr (LY::kWindowInSmem) {
+    for (int i = tid; i < NFFT; i += kThreads) s_window[i] = p.window[i];
+  }
   if constexpr (NFFT == 2048) {
     for (int i = tid; i < LY::kFoldN; i += kThreads) s_fold[i] = p.fold_tw[i];
   }
@@ -223,20 +234,34 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
 
   // per-lane constants kept in registers for the whole kernel
   constexpr int kPts = NFFT == 1024 ? 16 : 32;  // complex points per lane
-  float2 tw[kPts];                              // inter-pass twiddles W_{NFFT/2}^{lane*k1}
+  constexpr int kTwRegs = kLean ? 1 : kPts;
+  float2 tw[kTwRegs];                           // inter-pass twiddles W_{NFFT/2}^{lane*k1}
+  if constexpr (!kLean) {
 #pragma unroll
-  for (int k1 = 0; k1 < kPts; ++k1) tw[k1] = p.stage_tw[k1 * 32 + lane];
+    for (int k1 = 0; k1 < kPts; ++k1) tw[k1] = p.stage_tw[k1 * 32 + lane];
+  }
+  // lean variant: only W^{lane*{1,2,4,8}} stay resident, the other eleven are rebuilt per frame
+  const float2 w1 = p.stage_tw[1 * 32 + lane], w2 = p.stage_tw[2 * 32 + lane];
+  const float2 w4 = p.stage_tw[4 * 32 + lane], w8 = p.stage_tw[8 * 32 + lane];
+  float2 win[(NFFT == 1024 && !kLean) ? 16 : 1];  // window taps of this lane's samples
   float2 fold_base = make_float2(1.f, 0.f);     // W_1024^lane
-  if constexpr (NFFT == 1024) fold_base = p.fold_tw[lane];
-  // the window taps of this lane's samples are re-read from shared memory for every frame: keeping
-  // them in 32 registers starved the scheduler of temporaries under the 128-register cap
-  const float2* my_win = reinterpret_cast<const float2*>(s_window) + lane;
+  if constexpr (NFFT == 1024) {
+    if constexpr (!kLean) {
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const int idx = 2 * (32 * n1 + lane);
+        win[n1] = make_float2(p.window[idx], p.window[idx + 1]);
+      }
+    }
+    fold_base = p.fold_tw[lane];
+  }
+  const float2* my_win = reinterpret_cast<const float2*>(s_window) + lane;  // lean / 2048: taps re-read per frame
 
   const int padded_len = p.n_samples + 2 * p.pad_inner + 2 * p.pad_outer;
   const bool hop_even = (p.hop & 1) == 0;
   const bool row_vec_ok = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0) && ((p.row_stride & 3) == 0);
   unsigned long long edge_hits = 0;
-  uint32_t phase_bits = 0;  // parity to wait for on the staging barrier
+  uint32_t phase_bits = 0;  // bit b: parity to wait for on bars[b]
 
   auto describe = [&](int tile) {
     TileInfo ti;
@@ -256,15 +281,15 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
     ti.src0 = (long long)ti.row * p.row_stride + b0;
     return ti;
   };
-  // Start filling the wave buffer with the samples of a tile (the buffer must be free).
-  auto stage = [&](const TileInfo& ti) {
-    if (ti.frame_limit == 0) return;
-    float* wave = wave0;
+  // Start filling wave buffer b with the samples of a tile.
+  auto stage = [&](const TileInfo& ti, int b) {
+    if (ti.frame_limit == 0 || (p.debug_skip & 4)) return;
+    float* wave = wave0 + b * p.wave_len;
     if (ti.async) {
       if (tid == 0) {
         fence_proxy_async();  // earlier generic-proxy reads of this buffer are ordered before the async write
-        mbar_expect_tx(&bars[0], p.wave_len * 4);
-        bulk_copy_g2s(wave, p.wav + ti.src0, p.wave_len * 4, &bars[0]);
+        mbar_expect_tx(&bars[b], p.wave_len * 4);
+        bulk_copy_g2s(wave, p.wav + ti.src0, p.wave_len * 4, &bars[b]);
       }
     } else {
       const float* src = p.wav + (long long)ti.row * p.row_stride - p.src_base;
@@ -281,45 +306,55 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
   __syncthreads();  // constants + barrier init visible
   int tile = blockIdx.x;
   TileInfo cur = describe(tile < p.n_tiles ? tile : 0);
-  if (tile < p.n_tiles) stage(cur);
+  if (tile < p.n_tiles) stage(cur, 0);
 
-  for (; tile < p.n_tiles; tile += gridDim.x) {
-    const float* wave = wave0;
+  for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    const int b = LY::kWaveBufs == 2 ? (it & 1) : 0;
+    const float* wave = wave0 + b * p.wave_len;
     const bool dead = cur.frame_limit == 0;
 
-    // ---- 1. wait for this tile's samples
-    if (!dead) {
+    // ---- 1. this tile's samples are in wave[b]; start fetching the next tile
+    if (!dead && !(p.debug_skip & 4)) {
       if (cur.async) {
-        mbar_wait(&bars[0], phase_bits & 1u);
-        phase_bits ^= 1u;
+        mbar_wait(&bars[b], (phase_bits >> b) & 1u);
+        phase_bits ^= 1u << b;
       } else {
         __syncthreads();  // plain stores of all threads
       }
     }
     const bool has_next = tile + (int)gridDim.x < p.n_tiles;
     const TileInfo nxt = describe(has_next ? tile + (int)gridDim.x : tile);
+    if constexpr (LY::kWaveBufs == 2) {
+      if (has_next) stage(nxt, b ^ 1);  // double buffered: the next tile loads while this one computes
+    }
 
     // ---- 2. FFT -> magnitudes ------------------------------------------------
+    const int fft_frames = (p.debug_skip & 1) ? 0 : cur.frame_limit;
     if constexpr (NFFT == 1024) {
       const int h = lane >> 4;
       const int partner = mirror_lane512(lane);
 #pragma unroll 1
-      for (int fr = warp; fr < cur.frame_limit; fr += kWarps) {
+      for (int fr = warp; fr < fft_frames; fr += kWarps) {
         const float* fa = wave + fr * p.hop;
         float2 v[16];
         if (hop_even) {
           const float2* f2 = reinterpret_cast<const float2*>(fa);
 #pragma unroll
-          for (int n1 = 0; n1 < 16; ++n1) v[n1] = f2_mul(f2[32 * n1 + lane], my_win[32 * n1]);
+          for (int n1 = 0; n1 < 16; ++n1) {
+            if constexpr (kLean) v[n1] = f2_mul(f2[32 * n1 + lane], my_win[32 * n1]);
+            else v[n1] = f2_mul(f2[32 * n1 + lane], win[n1]);
+          }
         } else {
 #pragma unroll
           for (int n1 = 0; n1 < 16; ++n1) {
             const int idx = 2 * (32 * n1 + lane);
-            v[n1] = f2_mul(make_float2(fa[idx], fa[idx + 1]), my_win[32 * n1]);
+            if constexpr (kLean) v[n1] = f2_mul(make_float2(fa[idx], fa[idx + 1]), my_win[32 * n1]);
+            else v[n1] = f2_mul(make_float2(fa[idx], fa[idx + 1]), win[n1]);
           }
         }
         __syncwarp();  // previous frame's pass-2 reads of my_tile are done
-        fft512_pass1(v, tw, my_tile, lane);
+        if constexpr (kLean) fft512_pass1_pow(v, w1, w2, w4, w8, my_tile, lane);
+        else fft512_pass1(v, tw, my_tile, lane);
         __syncwarp();
         fft512_pass2(v, my_tile, lane);
         float2 send[8], recv[8], zlo[8], zhi[8];
@@ -336,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
       }
     } else {
 #pragma unroll 1
-      for (int fr = warp; fr < cur.frame_limit; fr += kWarps) {
+      for (int fr = warp; fr < fft_frames; fr += kWarps) {
         const float* fa = wave + fr * p.hop;
         float2 v[32];
 #pragma unroll
@@ -370,8 +405,9 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
       }
     }
     __syncthreads();
-    // the wave buffer is free: fetch the next tile under the mel phase
-    if (has_next) stage(nxt);
+    if constexpr (LY::kWaveBufs == 1) {
+      if (has_next) stage(nxt, 0);  // single buffer: it is free now, the copy flies under the mel phase
+    }
 
     // ---- 3. mel filterbank, log, quantise --------------------------------
     // One lane per frame, 32/TF adjacent channels side by side in a warp.  The host pads the spans
@@ -388,7 +424,8 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
       const int m0 = warp * kGroups + sub;
       const size_t ostep = (size_t)kStep * p.n_frames;
       size_t o = ((size_t)cur.row * p.n_mels + m0) * p.n_frames + t;
-      if (dead) {
+      if (p.debug_skip & 2) {
+      } else if (dead) {
         // nothing of this tile is valid audio: codes are the pad value, nothing else is written
         if constexpr (kCodes) {
 #pragma unroll 1
@@ -408,21 +445,15 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
           const float4* x4 = reinterpret_cast<const float4*>(mrow + (c.x & 0xffff));
           const float4* x4_end = x4 + (c.x >> 18);  // span length / 4: >= 1, identical across the warp
           float acc = 0.f;
-          float4 w = *w4++, x = *x4++;  // the loads of the next four bins are in flight during the FMAs
 #pragma unroll 1
-          while (x4 != x4_end) {
-            const float4 wn = *w4++, xn = *x4++;
+          do {
+            const float4 w = *w4++;
+            const float4 x = *x4++;
             acc = fmaf(w.x, x.x, acc);
             acc = fmaf(w.y, x.y, acc);
             acc = fmaf(w.z, x.z, acc);
             acc = fmaf(w.w, x.w, acc);
-            w = wn;
-            x = xn;
-          }
-          acc = fmaf(w.x, x.x, acc);
-          acc = fmaf(w.y, x.y, acc);
-          acc = fmaf(w.z, x.z, acc);
-          acc = fmaf(w.w, x.w, acc);
+          } while (x4 != x4_end);
           const float value = fast_log(fmaxf(acc, kLogClip));
           if constexpr (kLogmel) {
             if (live && in_row) p.logmel[o] = value;
@@ -453,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, NFFT == 1024 ? 2 : 1) dmel_fused_ker
         }
       }
     }
-    __syncthreads();  // mags are free again; plain-store staging of the next tile is visible
+    __syncthreads();  // mags and wave[b] are free again
     cur = nxt;
   }
 

@@ -94,11 +94,14 @@ def test_logmel_vs_oracle_other_geometries(d, kw):
 
 
 def test_launch_configuration_for_the_benchmark_geometry(d):
-    """configs[1] must get the 16-frame tile with two CTAs per SM (shared memory is sized to the byte for it)."""
-    tr = _transform(d, GOLDEN_GEOMETRY["cfg2_24k_128"])
-    info = tr.spectrogram.plan_for(torch.device("cuda", torch.cuda.current_device())).describe()
-    assert info["tile_frames"] == 16 and info["ctas_per_sm"] == 2, info
-    assert info["smem_bytes"] <= 115712
+    """configs[1] must get the register-lean 8-frame tile with three CTAs per SM (its shared memory is sized
+    to fit a third of the SM), and the 2048 geometry the one-CTA variant."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    info = _transform(d, GOLDEN_GEOMETRY["cfg2_24k_128"]).spectrogram.plan_for(dev).describe()
+    assert info["tile_frames"] == 8 and info["ctas_per_sm"] == 3, info
+    assert info["smem_bytes"] <= 233472 // 3 - 1024
+    info = _transform(d, GOLDEN_GEOMETRY["cfg5_44k_160"]).spectrogram.plan_for(dev).describe()
+    assert info["ctas_per_sm"] == 1, info
 
 
 def test_too_short_input_raises_like_the_reference(d):
