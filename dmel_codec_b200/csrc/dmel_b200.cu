@@ -61,6 +61,7 @@ struct dmel_plan {
   int nnz = 0;
   int n_chan_pad = 0;  // n_mels rounded up to the channel-group size 32 / tile_frames
   size_t smem_bytes = 0;
+  mutable unsigned smem_opt_in = 0;  // bit per output MODE whose kernel already has its dynamic-smem limit raised
   float* d_window = nullptr;
   float2* d_stage_tw = nullptr;
   float2* d_fold_tw = nullptr;
@@ -132,8 +133,11 @@ struct Launch {
   template <int NFFT, int TF, int OCC>
   cudaError_t operator()() const {
     auto kern = dmel::dmel_fused_kernel<NFFT, TF, MODE, OCC>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
-    if (e != cudaSuccess) return e;
+    if (!(plan->smem_opt_in & (1u << MODE))) {  // once per plan and output mode
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
+      if (e != cudaSuccess) return e;
+      plan->smem_opt_in |= 1u << MODE;
+    }
     kern<<<grid, dmel::kThreads, plan->smem_bytes, st>>>(*p);
     return cudaGetLastError();
   }
@@ -536,10 +540,10 @@ int dmel_encode_host_u8(dmel_plan* plan, const float* wav_host, long long n_rows
     DMEL_CUDA(cudaMalloc((void**)&plan->d_lo, plan->n_mels * sizeof(float)));
     DMEL_CUDA(cudaMalloc((void**)&plan->d_scale, plan->n_mels * sizeof(float)));
   }
-  // rows per chunk: a few MiB of waveform (DMEL_HOST_CHUNK_MB, default 4), so copies and kernels of
+  // rows per chunk: a few MiB of waveform (DMEL_HOST_CHUNK_MB, default 16), so copies and kernels of
   // neighbouring chunks overlap and the un-overlapped tail (last kernel + last D2H) stays short
   const long long row_bytes = n_samples * 4;
-  long long chunk_mb = 4;
+  long long chunk_mb = 16;
   if (const char* env = std::getenv("DMEL_HOST_CHUNK_MB")) chunk_mb = std::max(1, std::atoi(env));
   long long chunk_rows = std::max<long long>(1, (chunk_mb << 20) / row_bytes);
   chunk_rows = std::min(chunk_rows, n_rows);
@@ -577,8 +581,12 @@ int dmel_encode_host_u8(dmel_plan* plan, const float* wav_host, long long n_rows
     const long long rows = std::min(chunk_rows, n_rows - r0);
     cudaStream_t st = plan->streams[slot];
     // stream order already guarantees the slot's previous D2H finished before this H2D starts
-    DMEL_CUDA(cudaMemcpy2DAsync(plan->d_wav[slot], n_samples * 4, wav_host + r0 * row_stride, row_stride * 4,
-                                n_samples * 4, rows, cudaMemcpyHostToDevice, st));
+    if (row_stride == n_samples)
+      DMEL_CUDA(cudaMemcpyAsync(plan->d_wav[slot], wav_host + r0 * row_stride, (size_t)rows * n_samples * 4,
+                                cudaMemcpyHostToDevice, st));
+    else
+      DMEL_CUDA(cudaMemcpy2DAsync(plan->d_wav[slot], n_samples * 4, wav_host + r0 * row_stride, row_stride * 4,
+                                  n_samples * 4, rows, cudaMemcpyHostToDevice, st));
     const int32_t* len_dev = nullptr;
     if (lengths_host) {
       DMEL_CUDA(cudaMemcpyAsync(plan->d_len[slot], lengths_host + r0, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
