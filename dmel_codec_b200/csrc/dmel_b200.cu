@@ -86,7 +86,7 @@ struct Variant {
   int n_fft, tf, occ;
 };
 constexpr Variant kVariants[] = {{1024, 8, 3}, {1024, 16, 2}, {1024, 8, 2}, {1024, 16, 1}, {1024, 8, 1},
-                                 {2048, 16, 1}, {2048, 8, 1}};
+                                 {2048, 8, 2}, {2048, 16, 1}, {2048, 8, 1}};
 
 // calls f.template operator()<NFFT, TF, OCC>() for the variant (compile-time dispatch)
 template <typename F>
@@ -96,6 +96,7 @@ auto dispatch_variant(int n_fft, int tf, int occ, F&& f) {
     if (tf == 16) return occ == 2 ? f.template operator()<1024, 16, 2>() : f.template operator()<1024, 16, 1>();
     return occ == 2 ? f.template operator()<1024, 8, 2>() : f.template operator()<1024, 8, 1>();
   }
+  if (tf == 8 && occ == 2) return f.template operator()<2048, 8, 2>();
   return tf == 16 ? f.template operator()<2048, 16, 1>() : f.template operator()<2048, 8, 1>();
 }
 

@@ -330,6 +330,105 @@ DMEL_HD void unfold_store512(const float2 (&zlo)[8], const float2 (&zhi)[8], con
 }
 
 // =============================================================================
+// n_fft = 2048 on the 512-point core: X[k] = E[k] + W_2048^k O[k], with E and O the spectra of
+// the even and odd samples (two real sequences of 1024, each folded onto one 512-point FFT).
+// Halves the registers and the transpose tile of the 32-points-per-lane form below.
+// =============================================================================
+// cos / sin of 2*pi*j/64 for j = 0..8
+DMEL_HD constexpr float cos64(int j) {
+  switch (j) {
+    case 0: return 1.0f;
+    case 1: return 0.99518472667219693f;
+    case 2: return 0.98078528040323043f;
+    case 3: return 0.95694033573220882f;
+    case 4: return 0.92387953251128674f;
+    case 5: return 0.88192126434835505f;
+    case 6: return 0.83146961230254524f;
+    case 7: return 0.77301045336273699f;
+    default: return 0.70710678118654752f;
+  }
+}
+DMEL_HD constexpr float sin64(int j) {
+  switch (j) {
+    case 0: return 0.0f;
+    case 1: return 0.09801714032956060f;
+    case 2: return 0.19509032201612825f;
+    case 3: return 0.29028467725446233f;
+    case 4: return 0.38268343236508978f;
+    case 5: return 0.47139673682599764f;
+    case 6: return 0.55557023301960218f;
+    case 7: return 0.63439328416364549f;
+    default: return 0.70710678118654752f;
+  }
+}
+
+// Complex unfold of one bin pair of a real 1024-sequence from Z = FFT_512 of its fold:
+// A = Z[k], Bm = Z[512-k], w = W_1024^k.  Returns ek2 = 2 S[k] and em2 = 2 conj(S[512-k]).
+DMEL_HD void unfold_complex(float2 A, float2 Bm, float2 w, float2& ek2, float2& em2) {
+  const float2 P = f2_fma(Bm, make_float2(1.f, -1.f), A);
+  const float2 Q = f2_fma(f2_swap(A), make_float2(1.f, -1.f), f2_swap(Bm));
+  const float2 wq = cmul(w, Q);
+  ek2 = cadd(P, wq);
+  em2 = csub(P, wq);
+}
+// Spectrum halves of one lane: k = lane + 32 j -> S[k] (k2) and conj S[512-k] (m2), both times 2.
+struct HalfSpectrum {
+  float2 k2[8], m2[8];
+  float2 mid;  // lane 0 only: 2 S[256]
+};
+template <int J>
+DMEL_HD void unfold_complex_one(const float2 (&zlo)[8], const float2 (&recv)[8], float2 base1024, HalfSpectrum& s) {
+  unfold_complex(zlo[J], recv[J], mul_w32<J>(base1024), s.k2[J], s.m2[J]);
+}
+template <int... J>
+DMEL_HD void unfold_complex_all(const float2 (&zlo)[8], const float2 (&recv)[8], float2 base1024, HalfSpectrum& s,
+                                std::integer_sequence<int, J...>) {
+  (unfold_complex_one<J>(zlo, recv, base1024, s), ...);
+}
+// zlo/zhi/recv as in unfold_store512; base1024 = W_1024^lane.
+DMEL_HD void unfold_half_spectrum(const float2 (&zlo)[8], const float2 (&zhi)[8], const float2 (&recv)[8],
+                                  float2 base1024, HalfSpectrum& s) {
+  unfold_complex_all(zlo, recv, base1024, s, std::make_integer_sequence<int, 8>{});
+  float2 unused;
+  unfold_complex(zhi[0], zhi[0], make_float2(0.f, -1.f), s.mid, unused);  // k = 256 (meaningful on lane 0)
+}
+
+DMEL_HD float mag_from_twice(float2 x2) {
+  const float2 sq = f2_mul(x2, x2);
+  return fast_sqrt(fmaf(0.25f, sq.x + sq.y, kMagEps));
+}
+// Four magnitudes of the 2048-frame from one bin pair of E and O (all inputs are twice the value):
+//   X[k]       = E[k] + w O[k]                 X[1024-k] = conj(E[k] - w O[k])
+//   X[512-k]   = conj(Em + i w Om)             X[512+k]  = Em - i w Om       (Em = conj E[512-k] etc.)
+// with w = W_2048^k.
+template <int J>
+DMEL_HD void combine2048_one(const HalfSpectrum& e, const HalfSpectrum& o, float2 base2048, float* mrow, int lane) {
+  const float2 w = cmul_conj_cs(base2048, cos64(J), sin64(J));  // W_2048^{lane + 32 J} = base * W_64^J
+  const float2 t = cmul(w, o.k2[J]);
+  const float2 u = cmul(w, o.m2[J]);
+  const float2 iu = make_float2(-u.y, u.x);
+  const int k = lane + 32 * J;
+  mrow[k] = mag_from_twice(cadd(e.k2[J], t));
+  mrow[1024 - k] = mag_from_twice(csub(e.k2[J], t));
+  mrow[512 - k] = mag_from_twice(cadd(e.m2[J], iu));
+  mrow[512 + k] = mag_from_twice(csub(e.m2[J], iu));
+}
+template <int... J>
+DMEL_HD void combine2048_all(const HalfSpectrum& e, const HalfSpectrum& o, float2 base2048, float* mrow, int lane,
+                             std::integer_sequence<int, J...>) {
+  (combine2048_one<J>(e, o, base2048, mrow, lane), ...);
+}
+// Writes the 1025 magnitudes of the frame into mrow (this lane's share). base2048 = W_2048^lane.
+DMEL_HD void combine2048_store(const HalfSpectrum& e, const HalfSpectrum& o, float2 base2048, float* mrow, int lane) {
+  combine2048_all(e, o, base2048, mrow, lane, std::make_integer_sequence<int, 8>{});
+  if (lane == 0) {  // k = 256: W_2048^256 = (1 - i)/sqrt2
+    const float2 t = cmul_conj_cs(o.mid, 0.70710678118654752f, 0.70710678118654752f);
+    mrow[256] = mag_from_twice(cadd(e.mid, t));
+    mrow[768] = mag_from_twice(csub(e.mid, t));
+  }
+}
+
+// =============================================================================
 // n_fft = 2048 : 1024-point complex FFT, 32 points per lane
 // =============================================================================
 // Pass 1, lane n2:  v[n1] = z[32*n1 + n2].  Leaves Y[n2][k1] * W_1024^{n2*k1}

@@ -128,7 +128,11 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
 // registers (85-register budget) and the waveform tile is single-buffered.
 template <int NFFT, int TF, int OCC>
 struct FusedLayout {
-  static constexpr int kWaveBufs = OCC == 3 ? 1 : 2;
+  // n_fft 2048 with OCC == 2 runs each frame as two 512-point FFTs (even / odd samples) on the
+  // register-lean core; with OCC == 1 it is the 32-points-per-lane form (fallback when the lean
+  // layout does not fit twice into an SM).
+  static constexpr bool kSplit2048 = NFFT == 2048 && OCC == 2;
+  static constexpr int kWaveBufs = (OCC == 3 || kSplit2048) ? 1 : 2;
   static constexpr bool kWindowInSmem = NFFT == 2048 || OCC == 3;
   static constexpr int kBins = NFFT / 2 + 1;
   // row pitch 516 / 1028 floats: a multiple of 4 so a lane can fetch four bins of its frame with
@@ -136,7 +140,7 @@ struct FusedLayout {
   // 32 banks.  The host keeps every padded span inside its row.
   static constexpr int kMagPitch = kBins + 3;
   static constexpr int kMagFloats = TF * kMagPitch;
-  static constexpr int kTileF2 = NFFT == 1024 ? kTile512 : kTile1024;
+  static constexpr int kTileF2 = (NFFT == 1024 || kSplit2048) ? kTile512 : kTile1024;
   static constexpr int kFoldN = NFFT / 4 + 1;
   // byte offsets inside dynamic shared memory (all 16-byte aligned)
   static __host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
@@ -148,7 +152,7 @@ struct FusedLayout {
     return align16(window_off(wave_len) + (kWindowInSmem ? size_t(NFFT) * 4 : 0));
   }
   static __host__ __device__ size_t chan_off(int wave_len) {
-    return align16(fold_off(wave_len) + (NFFT == 2048 ? size_t(kFoldN) * 8 : 0));
+    return align16(fold_off(wave_len) + ((NFFT == 2048 && !kSplit2048) ? size_t(kFoldN) * 8 : 0));
   }
   // n_chan = channel count padded to the group size
   static __host__ __device__ size_t weights_off(int wave_len, int n_chan) {
@@ -175,11 +179,13 @@ struct TileInfo {
 
 template <int NFFT, int TF, int MODE, int OCC>
 __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedParams p) {
-  static_assert(OCC == 1 || OCC == 2 || (OCC == 3 && NFFT == 1024 && TF == 8), "occupancy variants");
+  static_assert(OCC == 1 || (OCC == 2 && (NFFT == 1024 || TF == 8)) || (OCC == 3 && NFFT == 1024 && TF == 8),
+                "occupancy variants");
   static_assert(NFFT == 1024 || NFFT == 2048, "register FFT cores: 512 and 1024 complex points");
   static_assert(TF == 32 || TF == 16 || TF == 8, "tile frames");
   using LY = FusedLayout<NFFT, TF, OCC>;
-  constexpr bool kLean = OCC == 3;  // register-lean variant
+  constexpr bool kSplit = LY::kSplit2048;
+  constexpr bool kLean = OCC == 3 || kSplit;  // register-lean variants: twiddles rebuilt, window in smem
   constexpr int kPitch = LY::kMagPitch;
   constexpr bool kCodes = (MODE & kOutCodes) != 0, kLogmel = (MODE & kOutLogmel) != 0;
   constexpr bool kStats = (MODE & kOutStats) != 0, kEdge = (MODE & kOutEdge) != 0;
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   if constexpr (LY::kWindowInSmem) {
     for (int i = tid; i < NFFT; i += kThreads) s_window[i] = p.window[i];
   }
-  if constexpr (NFFT == 2048) {
+  if constexpr (NFFT == 2048 && !kSplit) {
     for (int i = tid; i < LY::kFoldN; i += kThreads) s_fold[i] = p.fold_tw[i];
   }
   if (tid == 0) {
@@ -233,16 +239,18 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   }
 
   // per-lane constants kept in registers for the whole kernel
-  constexpr int kPts = NFFT == 1024 ? 16 : 32;  // complex points per lane
+  constexpr int kPts = (NFFT == 1024 || kSplit) ? 16 : 32;  // complex points per lane
   constexpr int kTwRegs = kLean ? 1 : kPts;
   float2 tw[kTwRegs];                           // inter-pass twiddles W_{NFFT/2}^{lane*k1}
   if constexpr (!kLean) {
 #pragma unroll
     for (int k1 = 0; k1 < kPts; ++k1) tw[k1] = p.stage_tw[k1 * 32 + lane];
   }
-  // lean variant: only W^{lane*{1,2,4,8}} stay resident, the other eleven are rebuilt per frame
-  const float2 w1 = p.stage_tw[1 * 32 + lane], w2 = p.stage_tw[2 * 32 + lane];
-  const float2 w4 = p.stage_tw[4 * 32 + lane], w8 = p.stage_tw[8 * 32 + lane];
+  // lean variants: only W_512^{lane*{1,2,4,8}} stay resident, the other eleven are rebuilt per frame
+  // (the n_fft 2048 table holds W_1024^{k1*lane}, so W_512^{lane*k} sits at row 2k)
+  constexpr int kRow = kSplit ? 2 : 1;
+  const float2 w1 = p.stage_tw[1 * kRow * 32 + lane], w2 = p.stage_tw[2 * kRow * 32 + lane];
+  const float2 w4 = p.stage_tw[4 * kRow * 32 + lane], w8 = p.stage_tw[8 * kRow * 32 + lane];
   float2 win[(NFFT == 1024 && !kLean) ? 16 : 1];  // window taps of this lane's samples
   float2 fold_base = make_float2(1.f, 0.f);     // W_1024^lane
   if constexpr (NFFT == 1024) {
@@ -254,6 +262,11 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
       }
     }
     fold_base = p.fold_tw[lane];
+  }
+  float2 base1024 = make_float2(1.f, 0.f), base2048 = make_float2(1.f, 0.f);  // W_1024^lane, W_2048^lane
+  if constexpr (kSplit) {
+    base1024 = p.stage_tw[1 * 32 + lane];
+    base2048 = p.fold_tw[lane];
   }
   const float2* my_win = reinterpret_cast<const float2*>(s_window) + lane;  // lean / 2048: taps re-read per frame
 
@@ -368,6 +381,55 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
         for (int j = 0; j < 8; ++j)
           recv[j] = make_float2(__shfl_sync(0xffffffffu, send[j].x, partner), __shfl_sync(0xffffffffu, send[j].y, partner));
         unfold_store512(zlo, zhi, recv, fold_base, mags + fr * kPitch, lane);
+      }
+    } else if constexpr (kSplit) {
+      const int h = lane >> 4;
+      const int partner = mirror_lane512(lane);
+      // one 512-point FFT of v, unfolded into the half spectrum of a real 1024-sequence
+      auto half = [&](float2 (&v)[16], HalfSpectrum& out) {
+        __syncwarp();
+        fft512_pass1_pow(v, w1, w2, w4, w8, my_tile, lane);
+        __syncwarp();
+        fft512_pass2(v, my_tile, lane);
+        float2 send[8], recv[8], zlo[8], zhi[8];
+        combine_send(v, h, send);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          recv[j] = make_float2(__shfl_xor_sync(0xffffffffu, send[j].x, 16), __shfl_xor_sync(0xffffffffu, send[j].y, 16));
+        combine_finish(v, recv, h, zlo, zhi);
+        mirror_send512(zlo, zhi, lane, send);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          recv[j] = make_float2(__shfl_sync(0xffffffffu, send[j].x, partner), __shfl_sync(0xffffffffu, send[j].y, partner));
+        unfold_half_spectrum(zlo, zhi, recv, base1024, out);
+      };
+      const bool hop_vec = (p.hop & 3) == 0;
+      const float4* win4 = reinterpret_cast<const float4*>(s_window) + lane;
+#pragma unroll 1
+      for (int fr = warp; fr < fft_frames; fr += kWarps) {
+        const float* fa = wave + fr * p.hop;
+        float2 v[16], odd[16];  // even samples x[4n], x[4n+2] and odd samples x[4n+1], x[4n+3] of this lane
+        if (hop_vec) {
+          const float4* f4 = reinterpret_cast<const float4*>(fa) + lane;
+#pragma unroll
+          for (int n1 = 0; n1 < 16; ++n1) {
+            const float4 x = f4[32 * n1], w = win4[32 * n1];
+            v[n1] = make_float2(x.x * w.x, x.z * w.z);
+            odd[n1] = make_float2(x.y * w.y, x.w * w.w);
+          }
+        } else {
+#pragma unroll
+          for (int n1 = 0; n1 < 16; ++n1) {
+            const int idx = 4 * (32 * n1 + lane);
+            const float4 w = win4[32 * n1];
+            v[n1] = make_float2(fa[idx] * w.x, fa[idx + 2] * w.z);
+            odd[n1] = make_float2(fa[idx + 1] * w.y, fa[idx + 3] * w.w);
+          }
+        }
+        HalfSpectrum e, o;
+        half(v, e);
+        half(odd, o);
+        combine2048_store(e, o, base2048, mags + fr * kPitch, lane);
       }
     } else {
 #pragma unroll 1

@@ -95,13 +95,29 @@ def test_logmel_vs_oracle_other_geometries(d, kw):
 
 def test_launch_configuration_for_the_benchmark_geometry(d):
     """configs[1] must get the register-lean 8-frame tile with three CTAs per SM (its shared memory is sized
-    to fit a third of the SM), and the 2048 geometry the one-CTA variant."""
+    to fit a third of the SM), and the 2048 geometry the two-CTA even/odd-split variant."""
     dev = torch.device("cuda", torch.cuda.current_device())
     info = _transform(d, GOLDEN_GEOMETRY["cfg2_24k_128"]).spectrogram.plan_for(dev).describe()
     assert info["tile_frames"] == 8 and info["ctas_per_sm"] == 3, info
     assert info["smem_bytes"] <= 233472 // 3 - 1024
     info = _transform(d, GOLDEN_GEOMETRY["cfg5_44k_160"]).spectrogram.plan_for(dev).describe()
-    assert info["ctas_per_sm"] == 1, info
+    assert info["tile_frames"] == 8 and info["ctas_per_sm"] == 2, info
+
+
+@pytest.mark.parametrize("occ", ["1", "2"])
+def test_fallback_kernel_variants_agree_with_golden(d, golden, occ, monkeypatch):
+    """The variants chosen when shared memory is tight (fewer CTAs per SM, other FFT forms) stay correct."""
+    monkeypatch.setenv("DMEL_OCC", occ)
+    for name in ("cfg2_24k_128", "cfg5_44k_160", "short_window"):
+        if occ == "2" and name == "cfg5_44k_160":
+            continue  # that is already the default variant
+        kw = GOLDEN_GEOMETRY[name]
+        tr = _transform(d, kw)
+        got = tr(torch.from_numpy(golden[name + "/wav"]).cuda())
+        info = tr.spectrogram.plan_for(got.device).describe()
+        assert info["ctas_per_sm"] == int(occ), info
+        ok, ratio = logmel_close(got.cpu(), torch.from_numpy(golden[name + "/logmel"]), REL_TOL)
+        assert ok, f"{name} occ={occ}: {ratio:.2f}x tolerance"
 
 
 def test_too_short_input_raises_like_the_reference(d):
