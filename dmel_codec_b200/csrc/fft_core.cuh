@@ -56,10 +56,11 @@ DMEL_HD constexpr float sin32(int q) { return q <= 8 ? cos32_q(8 - q) : cos32_q(
 // add/mul/fma.rn.f32x2, SASS FADD2/FMUL2/FFMA2) with free operand swizzles (swap halves, negate
 // one half, broadcast a scalar): a complex add is one instruction, a complex multiply two.
 // Build with -DDMEL_PACKED_F32X2 to use them.  Measured on B200 (profiles/history.md): warp
-// instructions per frame drop 1295 -> 1096, but a packed op holds the FMA pipe for two issue
-// cycles and IPC falls by the same factor; the scalar build is 1.5-2 % faster in every
-// configuration tried, so scalar FADD/FMUL/FFMA is the default.  Either way the host versions
-// spell out the same operations in the same order for tests/host_emul.cu.
+// instructions per frame drop 1496 -> 1201, but a packed op holds the FMA pipe for two issue
+// cycles (benchmarks/fp_issue_rate.cu: 3.9 scalar vs 2.0 packed warp-instructions/cycle/SM), IPC
+// falls by the same factor and the kernel time is identical (117.5 vs 117.4 us).  The scalar
+// form stays the default; either way the host versions spell out the same operations in the
+// same order for tests/host_emul.cu.
 #if !defined(__CUDA_ARCH__)
 #undef DMEL_PACKED_F32X2
 #endif
@@ -120,8 +121,8 @@ template <int Q>
 DMEL_HD float2 mul_w32(float2 d) {
   if constexpr (Q == 0) {
     return d;
-  } else if constexpr (Q == 8) {  // -i : (d.y, -d.x)
-    return f2_mul(f2_swap(d), make_float2(1.f, -1.f));
+  } else if constexpr (Q == 8) {  // -i : (d.y, -d.x); swap and sign ride on the consumer's operand modifiers
+    return make_float2(d.y, -d.x);
   } else {
     return cmul_conj_cs(d, cos32(Q), sin32(Q));
   }
