@@ -7,6 +7,7 @@ to the GPU box with the repo snapshot.
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -29,16 +30,35 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found: set NVCC or put /usr/local/cuda/bin on PATH")
 
 
+STAMP = OUT + ".srchash"  # content hash of the sources the .so was built from (mtimes do not survive copies)
+
+
+def source_hash() -> str:
+    h = hashlib.sha256()
+    for d in DEPS:
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("DMEL_NVCC_EXTRA", "").encode())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not os.path.exists(OUT):
+    if not (os.path.exists(OUT) and os.path.exists(STAMP)):
         return True
-    built = os.path.getmtime(OUT)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > built for d in DEPS)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return OUT
+    try:
+        find_nvcc()
+    except RuntimeError:
+        if os.path.exists(OUT) and not force:
+            return OUT  # no compiler on this box: use the library that travelled with the repo
+        raise
     extra = os.environ.get("DMEL_NVCC_EXTRA", "").split()  # e.g. -DDMEL_SCALAR_FP for A/B measurements
     cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-o", OUT, *[os.path.join(CSRC, s) for s in SOURCES]]
     if verbose:
@@ -49,6 +69,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
     if verbose:
         print(res.stderr)
+    with open(STAMP, "w") as f:
+        f.write(source_hash())
     return OUT
 
 
