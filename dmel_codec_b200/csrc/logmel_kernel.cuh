@@ -173,8 +173,11 @@ struct FusedLayout {
 struct TileInfo {
   int row, t0, n_valid;
   int frame_limit;  // frames of this tile worth computing (t0-relative), 0 = skip the tile
-  bool async;       // staged by the bulk-copy engine (interior, 16-byte aligned) or by plain loads
-  long long src0;   // sample offset of padded-row position t0*hop in the flat waveform, if interior
+  // staging: wave[bulk_lo, bulk_lo + bulk_n) comes from one bulk async copy (the samples that exist and
+  // need no reflection), the rest - nothing for interior tiles - from plain reflect-indexed loads
+  int bulk_lo, bulk_n;
+  bool manual;      // some of the tile is staged by plain loads (row ends, unaligned rows)
+  long long src0;   // flat waveform offset of wave[0]'s sample (valid inside the bulk range)
 };
 
 template <int NFFT, int TF, int MODE, int OCC>
@@ -290,24 +293,32 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
     ti.frame_limit = last < 0 ? 0 : (last > TF ? TF : last);
     const int s0 = (p.t_begin + ti.t0) * p.hop - p.pad_inner - p.pad_outer;  // virtual sample under the tile's first tap
     const int b0 = s0 - p.src_base;                                          // where that sample sits in the buffer
-    ti.async = row_vec_ok && s0 >= 0 && b0 >= 0 && (b0 & 3) == 0 && s0 + p.wave_len <= p.n_samples;
     ti.src0 = (long long)ti.row * p.row_stride + b0;
+    int lo = s0 < 0 ? ((-s0 + 3) & ~3) : 0;                                   // first wave index with a real sample
+    if (b0 + lo < 0) lo = (-b0 + 3) & ~3;                                     // ... that is resident in the buffer
+    int hi = p.n_samples - s0 < p.wave_len ? ((p.n_samples - s0) & ~3) : p.wave_len;  // one past the last
+    const bool can_bulk = row_vec_ok && p.pad_outer == 0 && (b0 & 3) == 0 && hi > lo;
+    ti.bulk_lo = can_bulk ? lo : 0;
+    ti.bulk_n = can_bulk ? hi - lo : 0;
+    ti.manual = !can_bulk || lo > 0 || hi < p.wave_len;
     return ti;
   };
   // Start filling wave buffer b with the samples of a tile.
   auto stage = [&](const TileInfo& ti, int b) {
     if (ti.frame_limit == 0 || (p.debug_skip & 4)) return;
     float* wave = wave0 + b * p.wave_len;
-    if (ti.async) {
-      if (tid == 0) {
-        fence_proxy_async();  // earlier generic-proxy reads of this buffer are ordered before the async write
-        mbar_expect_tx(&bars[b], p.wave_len * 4);
-        bulk_copy_g2s(wave, p.wav + ti.src0, p.wave_len * 4, &bars[b]);
-      }
-    } else {
+    if (ti.bulk_n && tid == 0) {
+      fence_proxy_async();  // earlier generic-proxy reads of this buffer are ordered before the async write
+      mbar_expect_tx(&bars[b], ti.bulk_n * 4);
+      bulk_copy_g2s(wave + ti.bulk_lo, p.wav + ti.src0 + ti.bulk_lo, ti.bulk_n * 4, &bars[b]);
+    }
+    if (ti.manual) {
       const float* src = p.wav + (long long)ti.row * p.row_stride - p.src_base;
       const int j0 = (p.t_begin + ti.t0) * p.hop;  // first position in the padded row
-      for (int i = tid; i < p.wave_len; i += kThreads) {
+      const int skip_lo = ti.bulk_lo, skip_hi = ti.bulk_lo + ti.bulk_n;
+      const int n_manual = p.wave_len - ti.bulk_n;
+      for (int q = tid; q < n_manual; q += kThreads) {
+        const int i = q < skip_lo ? q : q + (skip_hi - skip_lo);  // wave index outside the bulk range
         const int j = j0 + i;
         float x = 0.f;
         if (j < padded_len) x = __ldg(src + reflect_src(j, p.n_samples, p.pad_inner, p.pad_outer));
@@ -328,12 +339,11 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
 
     // ---- 1. this tile's samples are in wave[b]; start fetching the next tile
     if (!dead && !(p.debug_skip & 4)) {
-      if (cur.async) {
+      if (cur.bulk_n) {
         mbar_wait(&bars[b], (phase_bits >> b) & 1u);
         phase_bits ^= 1u << b;
-      } else {
-        __syncthreads();  // plain stores of all threads
       }
+      if (cur.manual) __syncthreads();  // plain stores of all threads
     }
     const bool has_next = tile + (int)gridDim.x < p.n_tiles;
     const TileInfo nxt = describe(has_next ? tile + (int)gridDim.x : tile);
