@@ -116,6 +116,17 @@ DMEL_HD float2 cmul_conj_cs(float2 d, float c, float s) {
   return f2_fma(f2_swap(d), make_float2(s, -s), f2_mul(d, make_float2(c, c)));
 }
 
+// p + q * (c - i s): the twiddle multiply folded into the butterfly's add (two packed / four scalar FMAs)
+DMEL_HD float2 cfma_conj_cs(float2 p, float2 q, float c, float s) {
+  return f2_fma(f2_swap(q), make_float2(s, -s), f2_fma(q, make_float2(c, c), p));
+}
+// p + q * w
+DMEL_HD float2 cfma(float2 p, float2 q, float2 w) {
+  return f2_fma(f2_swap(q), make_float2(-w.y, w.y), f2_fma(q, make_float2(w.x, w.x), p));
+}
+// 2p - r: the second output of a butterfly whose first output r = p + t is known (p - t = 2p - r)
+DMEL_HD float2 twice_minus(float2 p, float2 r) { return f2_fma(p, make_float2(2.f, 2.f), make_float2(-r.x, -r.y)); }
+
 // d * W_32^Q with the trivial rotations folded away at compile time
 template <int Q>
 DMEL_HD float2 mul_w32(float2 d) {
@@ -151,13 +162,44 @@ DMEL_HD void radix32(float2 (&a)[32]) {
   dif_stage<32, 2>(a, seq{});
   dif_stage<32, 1>(a, seq{});
 }
-// In-place forward 16-point DFT; X[k] == a[brev4(k)].
+// Decimation-in-time butterfly with the twiddle folded into the add:
+//   a[p] <- a[p] + W a[q],   a[q] <- a[p] - W a[q] = 2 a[p] - (a[p] + W a[q]),   W = W_{2H}^j = W_32^{j*16/H}
+// six FMAs where multiply-then-add/subtract takes eight; trivial W stay four adds.
+template <int N, int H, int I>
+DMEL_HD void dit_butterfly(float2 (&a)[N]) {
+  constexpr int blk = I / H, j = I % H;
+  constexpr int p = blk * 2 * H + j, q = p + H;
+  constexpr int Q = j * (16 / H);
+  const float2 u = a[p], w = a[q];
+  if constexpr (Q == 0) {
+    a[p] = cadd(u, w);
+    a[q] = csub(u, w);
+  } else if constexpr (Q == 8) {  // W = -i: W w = (w.y, -w.x)
+    a[p] = make_float2(u.x + w.y, u.y - w.x);
+    a[q] = make_float2(u.x - w.y, u.y + w.x);
+  } else {
+    const float2 r = cfma_conj_cs(u, w, cos32(Q), sin32(Q));
+    a[p] = r;
+    a[q] = twice_minus(u, r);
+  }
+}
+template <int N, int H, int... I>
+DMEL_HD void dit_stage(float2 (&a)[N], std::integer_sequence<int, I...>) {
+  (dit_butterfly<N, H, I>(a), ...);
+}
+// In-place forward 16-point DFT; X[k] == a[brev4(k)].  Decimation in time on a bit-reversed
+// copy; every index is a compile-time constant, so both permutations are register renamings.
 DMEL_HD void radix16(float2 (&a)[16]) {
   using seq = std::make_integer_sequence<int, 8>;
-  dif_stage<16, 8>(a, seq{});
-  dif_stage<16, 4>(a, seq{});
-  dif_stage<16, 2>(a, seq{});
-  dif_stage<16, 1>(a, seq{});
+  float2 b[16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) b[brev4(n)] = a[n];
+  dit_stage<16, 1>(b, seq{});
+  dit_stage<16, 2>(b, seq{});
+  dit_stage<16, 4>(b, seq{});
+  dit_stage<16, 8>(b, seq{});
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[brev4(k)] = b[k];
 }
 
 // Shared-memory transpose tile of one warp: rows of 32 complex, row pitch
@@ -198,8 +240,7 @@ constexpr float kMagEps = 1e-9f;  // reference utils/spectrogram.py:76
 DMEL_HD void folded_magnitudes(float2 A, float2 Bm, float2 w, float& mag_k, float& mag_mirror) {
   const float2 P = f2_fma(Bm, make_float2(1.f, -1.f), A);                            // 2E = (A.x+B.x, A.y-B.y)
   const float2 Q = f2_fma(f2_swap(A), make_float2(1.f, -1.f), f2_swap(Bm));          // 2O = (A.y+B.y, B.x-A.x)
-  const float2 wq = cmul(w, Q);
-  const float2 p = cadd(P, wq), m = csub(P, wq);
+  const float2 p = cfma(P, Q, w), m = twice_minus(P, p);
   const float2 pp = f2_mul(p, p), mm = f2_mul(m, m);
   mag_k = fast_sqrt(fmaf(0.25f, pp.x + pp.y, kMagEps));
   mag_mirror = fast_sqrt(fmaf(0.25f, mm.x + mm.y, kMagEps));
@@ -284,9 +325,8 @@ DMEL_HD void combine_one(const float2 (&v)[16], const float2 (&recv)[8], int h, 
   const float2 b = h ? v[brev4(2 * J + 1)] : recv[J];    // G_1[q] for h = 0 (q even), -G_1[q] for h = 1 (q odd)
   const float c = h ? -cos32(2 * J + 1) : cos32(2 * J);  // W_32^q = c - i s, sign of the rotated read folded in
   const float s = h ? -sin32(2 * J + 1) : sin32(2 * J);
-  const float2 t = cmul_conj_cs(b, c, s);
-  zlo[J] = cadd(a, t);
-  zhi[J] = csub(a, t);
+  zlo[J] = cfma_conj_cs(a, b, c, s);
+  zhi[J] = twice_minus(a, zlo[J]);
 }
 template <int... J>
 DMEL_HD void combine_all(const float2 (&v)[16], const float2 (&recv)[8], int h, float2 (&zlo)[8], float2 (&zhi)[8],
@@ -368,9 +408,8 @@ DMEL_HD constexpr float sin64(int j) {
 DMEL_HD void unfold_complex(float2 A, float2 Bm, float2 w, float2& ek2, float2& em2) {
   const float2 P = f2_fma(Bm, make_float2(1.f, -1.f), A);
   const float2 Q = f2_fma(f2_swap(A), make_float2(1.f, -1.f), f2_swap(Bm));
-  const float2 wq = cmul(w, Q);
-  ek2 = cadd(P, wq);
-  em2 = csub(P, wq);
+  ek2 = cfma(P, Q, w);
+  em2 = twice_minus(P, ek2);
 }
 // Spectrum halves of one lane: k = lane + 32 j -> S[k] (k2) and conj S[512-k] (m2), both times 2.
 struct HalfSpectrum {
@@ -405,14 +444,14 @@ DMEL_HD float mag_from_twice(float2 x2) {
 template <int J>
 DMEL_HD void combine2048_one(const HalfSpectrum& e, const HalfSpectrum& o, float2 base2048, float* mrow, int lane) {
   const float2 w = cmul_conj_cs(base2048, cos64(J), sin64(J));  // W_2048^{lane + 32 J} = base * W_64^J
-  const float2 t = cmul(w, o.k2[J]);
-  const float2 u = cmul(w, o.m2[J]);
-  const float2 iu = make_float2(-u.y, u.x);
+  const float2 iw = make_float2(-w.y, w.x);
+  const float2 xk = cfma(e.k2[J], o.k2[J], w);    // E + w O
+  const float2 xm = cfma(e.m2[J], o.m2[J], iw);   // Em + i w Om
   const int k = lane + 32 * J;
-  mrow[k] = mag_from_twice(cadd(e.k2[J], t));
-  mrow[1024 - k] = mag_from_twice(csub(e.k2[J], t));
-  mrow[512 - k] = mag_from_twice(cadd(e.m2[J], iu));
-  mrow[512 + k] = mag_from_twice(csub(e.m2[J], iu));
+  mrow[k] = mag_from_twice(xk);
+  mrow[1024 - k] = mag_from_twice(twice_minus(e.k2[J], xk));
+  mrow[512 - k] = mag_from_twice(xm);
+  mrow[512 + k] = mag_from_twice(twice_minus(e.m2[J], xm));
 }
 template <int... J>
 DMEL_HD void combine2048_all(const HalfSpectrum& e, const HalfSpectrum& o, float2 base2048, float* mrow, int lane,
