@@ -14,7 +14,7 @@ from ctypes import (POINTER, c_char_p, c_float, c_int, c_int32, c_longlong, c_ui
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DMEL_LIB") or os.path.join(_HERE, "libdmel_b200.so")  # DMEL_LIB: A/B builds
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = -1, -2, -3, -4
 
 # name -> (restype, argtypes); mirrors include/dmel_b200.h one to one
@@ -33,6 +33,14 @@ SIGNATURES = {
     "dmel_encode_frames_u8": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_longlong,
                                       c_longlong, c_longlong, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                       c_void_p]),
+    "dmel_stream_create": (c_int, [c_void_p, c_int, c_longlong, POINTER(c_void_p)]),
+    "dmel_stream_destroy": (None, [c_void_p]),
+    "dmel_stream_reset": (c_int, [c_void_p]),
+    "dmel_stream_pending": (c_longlong, [c_void_p, c_longlong, c_int]),
+    "dmel_stream_push": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_int, c_void_p,
+                                 c_longlong, POINTER(c_longlong), c_void_p]),
+    "dmel_stream_flush": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_longlong, POINTER(c_longlong),
+                                  c_void_p]),
     "dmel_encode_host_u8": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_void_p,
                                     c_void_p, c_void_p, c_int, c_void_p]),
     "dmel_quantize_u8": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_int,

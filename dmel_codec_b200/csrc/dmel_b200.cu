@@ -518,6 +518,146 @@ int dmel_encode_frames_u8(dmel_plan* plan, const float* wav_dev, long long n_row
   return DMEL_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Streaming encoder state (BASELINE configs[3]): per-stream history buffer on the device, counters
+// on the host.  One push = one copy of the chunk into the buffer + one windowed launch.
+// ---------------------------------------------------------------------------
+struct dmel_stream {
+  dmel_plan* plan = nullptr;
+  int n_streams = 0;
+  long long capacity = 0;  // samples per stream row (multiple of 4)
+  float* buf = nullptr;    // (n_streams, capacity)
+  float* scratch = nullptr;  // same shape, only for overlapping compactions
+  long long base = 0;      // virtual sample index of buf[:, 0]
+  long long seen = 0;      // samples received per stream
+  long long t_next = 0;    // next frame to emit
+};
+
+namespace {
+
+// frames that are complete once `seen` samples have arrived (their last tap is inside the data)
+long long stream_frames_ready(const dmel_stream* s, long long seen) {
+  const dmel_plan* pl = s->plan;
+  if (seen + pl->pad_inner < pl->n_fft || seen <= pl->pad_inner) return 0;
+  return (seen + pl->pad_inner - pl->n_fft) / pl->hop + 1;
+}
+
+int stream_emit(dmel_stream* s, long long t_end, const float* lo_dev, const float* scale_dev, int n_bins,
+                uint8_t* codes_dev, long long codes_frames, long long* n_frames_out, void* stream) {
+  const long long count = t_end - s->t_next;
+  if (n_frames_out) *n_frames_out = count > 0 ? count : 0;
+  if (count <= 0) return DMEL_OK;
+  if (!codes_dev || codes_frames != count)
+    return fail(DMEL_ERR_INVALID, "codes buffer holds %lld frames per channel, this call emits %lld "
+                "(size it with dmel_stream_pending)", codes_frames, count);
+  int rc = dmel_encode_frames_u8(s->plan, s->buf, s->n_streams, s->capacity, s->base, s->seen, s->t_next, count,
+                                 lo_dev, scale_dev, n_bins, codes_dev, nullptr, stream);
+  if (rc == DMEL_OK) s->t_next = t_end;
+  return rc;
+}
+
+}  // namespace
+
+int dmel_stream_create(dmel_plan* plan, int n_streams, long long capacity_samples, dmel_stream** out) {
+  if (!out) return fail(DMEL_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (!plan) return fail(DMEL_ERR_INVALID, "plan is null");
+  if (plan->pad_outer) return fail(DMEL_ERR_UNSUPPORTED, "streaming with center=True is not supported");
+  if (n_streams < 1) return fail(DMEL_ERR_INVALID, "n_streams must be >= 1, got %d", n_streams);
+  dmel_stream* s = new (std::nothrow) dmel_stream();
+  if (!s) return fail(DMEL_ERR_INVALID, "out of host memory");
+  s->plan = plan;
+  s->n_streams = n_streams;
+  s->capacity = std::max<long long>(capacity_samples, 4LL * plan->n_fft) / 4 * 4;
+  DeviceGuard guard(plan->device);
+  const size_t bytes = (size_t)n_streams * s->capacity * sizeof(float);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&s->buf), bytes);
+  if (e == cudaSuccess) e = cudaMemset(s->buf, 0, bytes);
+  if (e != cudaSuccess) {
+    cudaFree(s->buf);
+    delete s;
+    return fail(DMEL_ERR_CUDA, "stream buffer allocation failed: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return DMEL_OK;
+}
+
+void dmel_stream_destroy(dmel_stream* s) {
+  if (!s) return;
+  DeviceGuard guard(s->plan->device);
+  cudaFree(s->buf);
+  cudaFree(s->scratch);
+  delete s;
+}
+
+int dmel_stream_reset(dmel_stream* s) {
+  if (!s) return fail(DMEL_ERR_INVALID, "stream is null");
+  s->base = s->seen = s->t_next = 0;
+  return DMEL_OK;
+}
+
+long long dmel_stream_pending(const dmel_stream* s, long long n_incoming, int at_end) {
+  if (!s || n_incoming < 0) return -1;
+  const long long seen = s->seen + n_incoming;
+  const long long t_end = at_end ? num_frames(s->plan, seen) : stream_frames_ready(s, seen);
+  return std::max<long long>(t_end - s->t_next, 0);
+}
+
+int dmel_stream_push(dmel_stream* s, const float* chunk, long long n, long long chunk_stride,
+                     const float* lo_dev, const float* scale_dev, int n_bins, uint8_t* codes_dev,
+                     long long codes_frames, long long* n_frames_out, void* stream) {
+  if (!s) return fail(DMEL_ERR_INVALID, "stream is null");
+  if (n_frames_out) *n_frames_out = 0;
+  if (n < 0 || (n > 0 && (!chunk || chunk_stride < n)))
+    return fail(DMEL_ERR_INVALID, "bad chunk: n=%lld stride=%lld", n, chunk_stride);
+  cudaStream_t st = (cudaStream_t)stream;
+  DeviceGuard guard(s->plan->device);
+  if (s->seen - s->base + n > s->capacity) {
+    // drop the samples no future frame needs; the new base stays 16-byte aligned
+    long long keep_from = std::max<long long>(0, s->t_next * s->plan->hop - s->plan->pad_inner) / 4 * 4;
+    keep_from = std::max(keep_from, s->base);
+    const long long live = s->seen - keep_from, shift = keep_from - s->base;
+    if (live + n > s->capacity)
+      return fail(DMEL_ERR_INVALID, "chunk of %lld samples does not fit a stream buffer of %lld (%lld live)", n,
+                  s->capacity, live);
+    if (shift > 0 && live > 0) {
+      const size_t pitch = (size_t)s->capacity * sizeof(float), width = (size_t)live * sizeof(float);
+      if (live <= shift) {
+        DMEL_CUDA(cudaMemcpy2DAsync(s->buf, pitch, s->buf + shift, pitch, width, s->n_streams, cudaMemcpyDeviceToDevice, st));
+      } else {  // source and destination overlap: go through the scratch copy
+        if (!s->scratch) DMEL_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->scratch), (size_t)s->n_streams * pitch));
+        DMEL_CUDA(cudaMemcpy2DAsync(s->scratch, pitch, s->buf + shift, pitch, width, s->n_streams, cudaMemcpyDeviceToDevice, st));
+        DMEL_CUDA(cudaMemcpy2DAsync(s->buf, pitch, s->scratch, pitch, width, s->n_streams, cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    s->base = keep_from;
+  }
+  if (n > 0) {
+    float* dst = s->buf + (s->seen - s->base);
+    if (s->n_streams == 1) {
+      DMEL_CUDA(cudaMemcpyAsync(dst, chunk, (size_t)n * sizeof(float), cudaMemcpyDefault, st));
+    } else {
+      DMEL_CUDA(cudaMemcpy2DAsync(dst, (size_t)s->capacity * sizeof(float), chunk, (size_t)chunk_stride * sizeof(float),
+                                  (size_t)n * sizeof(float), s->n_streams, cudaMemcpyDefault, st));
+    }
+    s->seen += n;
+  }
+  return stream_emit(s, stream_frames_ready(s, s->seen), lo_dev, scale_dev, n_bins, codes_dev, codes_frames, n_frames_out,
+                     stream);
+}
+
+int dmel_stream_flush(dmel_stream* s, const float* lo_dev, const float* scale_dev, int n_bins, uint8_t* codes_dev,
+                      long long codes_frames, long long* n_frames_out, void* stream) {
+  if (!s) return fail(DMEL_ERR_INVALID, "stream is null");
+  if (n_frames_out) *n_frames_out = 0;
+  if (s->seen <= s->plan->pad_inner)
+    return fail(DMEL_ERR_INVALID, "stream of %lld samples is shorter than the reflect pad %d", s->seen, s->plan->pad_inner);
+  int rc = stream_emit(s, num_frames(s->plan, s->seen), lo_dev, scale_dev, n_bins, codes_dev, codes_frames, n_frames_out,
+                       stream);
+  if (rc == DMEL_OK) s->base = s->seen = s->t_next = 0;
+  return rc;
+}
+
 int dmel_encode_host_u8(dmel_plan* plan, const float* wav_host, long long n_rows, long long n_samples,
                         long long row_stride, const int32_t* lengths_host, const float* lo_host,
                         const float* scale_host, int n_bins, uint8_t* codes_host) {

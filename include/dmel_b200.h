@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DMEL_ABI_VERSION 1
+#define DMEL_ABI_VERSION 2
 
 #define DMEL_OK 0
 #define DMEL_ERR_INVALID (-1)     /* bad argument (shape, null pointer, L <= reflect pad ...) */
@@ -38,6 +38,7 @@ extern "C" {
 #define DMEL_ERR_NO_DEVICE (-4)   /* no CUDA device: there is no CPU fallback */
 
 typedef struct dmel_plan dmel_plan;
+typedef struct dmel_stream dmel_stream;
 
 int dmel_abi_version(void);
 const char* dmel_last_error(void);
@@ -104,6 +105,28 @@ int dmel_encode_frames_u8(dmel_plan* plan, const float* wav_dev, long long n_row
                           long long src_base, long long n_samples, long long t_begin, long long t_count,
                           const float* lo_dev, const float* scale_dev, int n_bins,
                           uint8_t* codes_dev, float* logmel_dev, void* stream);
+
+/* Streaming encoder (BASELINE configs[3], 80 ms chunks): a lock-step batch of n_streams audio
+ * streams with a device-side history buffer of capacity_samples per stream.  The reference has no
+ * streaming mode; the contract is that the codes of all pushes and the final flush, concatenated
+ * along T, equal dmel_encode_u8 on the whole waveform bit for bit (reference
+ * utils/spectrogram.py:41-81 applied to the complete row).
+ *   dmel_stream_pending : frames the next push of n_incoming samples (at_end = 0) or the flush
+ *                         (at_end = 1, n_incoming = 0) will emit; size the codes buffer with it.
+ *   dmel_stream_push    : appends chunk ((n_streams, chunk_stride >= n) float32, device OR host
+ *                         memory) and encodes every frame whose last tap has arrived into
+ *                         codes_dev (n_streams, n_mels, codes_frames); codes_frames must equal
+ *                         dmel_stream_pending.  One copy + one kernel launch on `stream`.
+ *   dmel_stream_flush   : end of stream: the remaining frames (right-edge reflection), then reset. */
+int dmel_stream_create(dmel_plan* plan, int n_streams, long long capacity_samples, dmel_stream** out);
+void dmel_stream_destroy(dmel_stream* s);
+int dmel_stream_reset(dmel_stream* s);
+long long dmel_stream_pending(const dmel_stream* s, long long n_incoming, int at_end);
+int dmel_stream_push(dmel_stream* s, const float* chunk, long long n, long long chunk_stride,
+                     const float* lo_dev, const float* scale_dev, int n_bins,
+                     uint8_t* codes_dev, long long codes_frames, long long* n_frames_out, void* stream);
+int dmel_stream_flush(dmel_stream* s, const float* lo_dev, const float* scale_dev, int n_bins,
+                      uint8_t* codes_dev, long long codes_frames, long long* n_frames_out, void* stream);
 
 /* Same as dmel_encode_u8 with HOST buffers: chunks rows through pinned staging,
  * overlapping H2D, kernel and D2H on internal streams; returns when codes_host

@@ -345,3 +345,24 @@ def test_streaming_equals_offline(d, chunking, n_streams):
     # the encoder is reusable after flush()
     again = torch.cat([enc.push(wav[:, 0, :4000]), enc.flush()], dim=2)
     assert torch.equal(again, tok.encode(wav[:, :, :4000])[0])
+
+
+def test_streaming_host_chunks_and_errors(d):
+    """Chunks may come straight from host memory; misuse raises like the offline path."""
+    from dmel_codec_b200 import synth
+    kw = GOLDEN_GEOMETRY["cfg1_16k_80"]
+    n = 16000 + 77
+    wav = synth.batch(range(710, 712), n, 16000, "speech")
+    tok = _tokenizer(d, kw, 16)
+    tok.calibrate([wav.cuda()])
+    want, _ = tok.encode(wav.cuda())
+    enc = d.DMelStreamEncoder(tok, n_streams=2, capacity_samples=4096)
+    parts = [enc.push(wav[:, 0, at:at + 1280].contiguous()) for at in range(0, n, 1280)]  # CPU tensors
+    parts.append(enc.flush())
+    assert torch.equal(torch.cat(parts, dim=2), want)
+    with pytest.raises(ValueError):
+        enc.flush()  # nothing received since the reset: shorter than the reflect pad
+    with pytest.raises(ValueError):
+        enc.push(torch.zeros(3, 10))  # wrong number of streams
+    with pytest.raises(ValueError):
+        enc.push(torch.zeros(2, 1 << 20))  # does not fit the history buffer
