@@ -149,16 +149,19 @@ cudaError_t launch_fused_mode(const dmel_plan* plan, const FusedParams& p, int g
   return dispatch_variant(plan->n_fft, plan->tile_frames, plan->ctas_per_sm, Launch<MODE>{plan, &p, grid, st});
 }
 
-cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st) {
+cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st,
+                             bool bf16_logmel = false) {
   using namespace dmel;
   int mode = 0;
   if (p.codes) mode |= kOutCodes;
   if (p.logmel) mode |= kOutLogmel;
   if (p.run_min) mode |= kOutStats;
   if (p.near_edge) mode |= kOutEdge;
+  if (bf16_logmel) mode |= kOutBf16;
   switch (mode) {
     case kOutCodes: return launch_fused_mode<kOutCodes>(plan, p, grid, st);
     case kOutLogmel: return launch_fused_mode<kOutLogmel>(plan, p, grid, st);
+    case kOutLogmel | kOutBf16: return launch_fused_mode<kOutLogmel | kOutBf16>(plan, p, grid, st);
     case kOutStats: return launch_fused_mode<kOutStats>(plan, p, grid, st);
     case kOutCodes | kOutLogmel: return launch_fused_mode<kOutCodes | kOutLogmel>(plan, p, grid, st);
     case kOutCodes | kOutEdge: return launch_fused_mode<kOutCodes | kOutEdge>(plan, p, grid, st);
@@ -448,6 +451,24 @@ int dmel_logmel_f32(dmel_plan* plan, const float* wav_dev, long long n_rows, lon
   p.logmel = logmel_dev;
   DeviceGuard guard(plan->device);
   DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream));
+  return DMEL_OK;
+}
+
+int dmel_logmel_masked(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
+                       long long row_stride, const int32_t* lengths_dev, int out_dtype, void* out_dev, void* stream) {
+  FusedParams p;
+  int grid = 0;
+  int rc = prepare_fused(plan, wav_dev, n_rows, n_samples, row_stride, &p, &grid);
+  if (rc != DMEL_OK) return rc;
+  if (!out_dev) return fail(DMEL_ERR_INVALID, "out_dev is null");
+  if (out_dtype != DMEL_DTYPE_F32 && out_dtype != DMEL_DTYPE_BF16)
+    return fail(DMEL_ERR_INVALID, "out_dtype must be DMEL_DTYPE_F32 or DMEL_DTYPE_BF16, got %d", out_dtype);
+  if (n_rows == 0) return DMEL_OK;
+  p.logmel = static_cast<float*>(out_dev);
+  p.lengths = lengths_dev;
+  p.mask_invalid = lengths_dev != nullptr;
+  DeviceGuard guard(plan->device);
+  DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream, out_dtype == DMEL_DTYPE_BF16));
   return DMEL_OK;
 }
 

@@ -18,6 +18,7 @@
 // out; constants come from L2.
 #pragma once
 #include <cstdint>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "fft_core.cuh"
@@ -33,6 +34,7 @@ constexpr int kOutCodes = 1;
 constexpr int kOutLogmel = 2;
 constexpr int kOutStats = 4;
 constexpr int kOutEdge = 8;  // count values within edge_eps of an interior bin edge (needs kOutCodes)
+constexpr int kOutBf16 = 16;  // the log-mel output tensor is bfloat16 (needs kOutLogmel)
 
 struct FusedParams {
   const float* wav;         // (B, row_stride) device
@@ -57,7 +59,8 @@ struct FusedParams {
   const int2* chan;         // (n_chan_pad) {first bin | count << 16 (both mult. of 4, count equal within a group), weight offset}
   const float* weights;
   const int* lengths;       // valid samples per row, or null
-  float* logmel;            // (B, M, T)            [kOutLogmel]
+  float* logmel;            // (B, M, T)            [kOutLogmel]; __nv_bfloat16 with kOutBf16
+  int mask_invalid;         // log-mel of frames at or past lengths[b] / hop is written as 0 (the caller's mel * mask)
   unsigned char* codes;     // (B, M, T)            [kOutCodes]
   const float* q_lo;        // (M)                  [kOutCodes]
   const float* q_scale;     // (M)  K / (hi - lo)   [kOutCodes]
@@ -192,6 +195,12 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   constexpr int kPitch = LY::kMagPitch;
   constexpr bool kCodes = (MODE & kOutCodes) != 0, kLogmel = (MODE & kOutLogmel) != 0;
   constexpr bool kStats = (MODE & kOutStats) != 0, kEdge = (MODE & kOutEdge) != 0;
+  constexpr bool kBf16 = (MODE & kOutBf16) != 0;
+  static_assert(!kBf16 || kLogmel, "kOutBf16 qualifies the log-mel output");
+  auto store_logmel = [&](size_t o, float v) {
+    if constexpr (kBf16) reinterpret_cast<__nv_bfloat16*>(p.logmel)[o] = __float2bfloat16_rn(v);
+    else p.logmel[o] = v;
+  };
 
   extern __shared__ __align__(16) unsigned char smem[];
   float2* tiles = reinterpret_cast<float2*>(smem);
@@ -288,8 +297,8 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
       const int nv = p.lengths[ti.row] / p.hop - p.t_begin;
       ti.n_valid = nv < 0 ? 0 : (nv < p.n_frames ? nv : p.n_frames);
     }
-    // log-mel output covers every frame of the row; codes / statistics only the valid ones
-    const int last = (kLogmel ? p.n_frames : ti.n_valid) - ti.t0;
+    // log-mel output covers every frame of the row (unless masked); codes / statistics only the valid ones
+    const int last = ((kLogmel && !p.mask_invalid) ? p.n_frames : ti.n_valid) - ti.t0;
     ti.frame_limit = last < 0 ? 0 : (last > TF ? TF : last);
     const int s0 = (p.t_begin + ti.t0) * p.hop - p.pad_inner - p.pad_outer;  // virtual sample under the tile's first tap
     const int b0 = s0 - p.src_base;                                          // where that sample sits in the buffer
@@ -498,11 +507,14 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
       size_t o = ((size_t)cur.row * p.n_mels + m0) * p.n_frames + t;
       if (p.debug_skip & 2) {
       } else if (dead) {
-        // nothing of this tile is valid audio: codes are the pad value, nothing else is written
-        if constexpr (kCodes) {
+        // nothing of this tile is valid audio: codes are the pad value, masked log-mel is zero
+        if constexpr (kCodes || kLogmel) {
 #pragma unroll 1
           for (int m = m0; m < p.n_mels; m += kStep, o += ostep)
-            if (in_row) p.codes[o] = 0;
+            if (in_row) {
+              if constexpr (kCodes) p.codes[o] = 0;
+              if constexpr (kLogmel) store_logmel(o, 0.f);
+            }
         }
       } else {
         const int2* cp = s_chan + m0;
@@ -528,7 +540,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
           } while (x4 != x4_end);
           const float value = fast_log(fmaxf(acc, kLogClip));
           if constexpr (kLogmel) {
-            if (live && in_row) p.logmel[o] = value;
+            if (live && in_row) store_logmel(o, (p.mask_invalid && !valid) ? 0.f : value);
           }
           if constexpr (kCodes) {
             const float sc = *scp;

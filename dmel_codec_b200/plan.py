@@ -95,6 +95,23 @@ class Plan:
             _stream_ptr(rows.device)))
         return out
 
+    def logmel_masked(self, wav: torch.Tensor, lengths: Optional[torch.Tensor],
+                      dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        """Log-mel in ``dtype`` (float32 or bfloat16) with frames at or past ``lengths // hop``
+        zeroed, in one launch (``dmel_logmel_masked``)."""
+        _require_cuda(wav, "audio")
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError(f"dtype must be torch.float32 or torch.bfloat16, got {dtype}")
+        rows = as_rows(wav)
+        b, n = rows.shape
+        t = self._frames_or_raise(n)
+        out = torch.empty((b, self.n_mels, t), dtype=dtype, device=rows.device)
+        len_ptr = self._lengths_ptr(lengths, b, rows.device)
+        _native.check(_native.load().dmel_logmel_masked(
+            self._handle, rows.data_ptr(), b, n, rows.stride(0) if b > 1 else n, len_ptr[0],
+            1 if dtype == torch.bfloat16 else 0, out.data_ptr(), _stream_ptr(rows.device)))
+        return out
+
     # -- calibration pass ---------------------------------------------------
     def update_minmax(self, wav: torch.Tensor, lengths: Optional[torch.Tensor], run_min: torch.Tensor,
                       run_max: torch.Tensor) -> None:

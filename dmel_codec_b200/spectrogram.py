@@ -83,3 +83,16 @@ class LogMelSpectrogram(nn.Module):
             import torchaudio.functional as AF  # off the hot path; no shipped caller passes sample_rate
             x = AF.resample(x, orig_freq=sample_rate, new_freq=self.sample_rate)
         return self.spectrogram(x)
+
+    @torch.no_grad()
+    def masked(self, audios: Tensor, audio_lengths: Tensor, dtype: torch.dtype = torch.float32):
+        """``(mels, mel_lengths)`` as ``VQGAN.encode_unquantized`` builds them before the encoder
+        (reference models/codec_lit_modules.py:486-507): log-mel cast to ``dtype`` with the frames at
+        or past ``audio_lengths // hop_length`` zeroed — transform, cast and ``sequence_mask``
+        multiply in one kernel launch, padded frames never computed.  The caller's group view
+        ``mels.view(B * G, n_mels // G, T)`` needs no copy."""
+        if not audios.is_cuda:
+            raise RuntimeError("dmel_codec_b200.LogMelSpectrogram needs a CUDA tensor (no CPU fallback); "
+                               f"got device {audios.device}")
+        mels = self.spectrogram.plan_for(audios.device).logmel_masked(audios, audio_lengths, dtype)
+        return mels, audio_lengths // self.hop_length

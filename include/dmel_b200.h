@@ -29,13 +29,16 @@
 extern "C" {
 #endif
 
-#define DMEL_ABI_VERSION 2
+#define DMEL_ABI_VERSION 3
 
 #define DMEL_OK 0
 #define DMEL_ERR_INVALID (-1)     /* bad argument (shape, null pointer, L <= reflect pad ...) */
 #define DMEL_ERR_UNSUPPORTED (-2) /* geometry this build has no kernel for */
 #define DMEL_ERR_CUDA (-3)        /* CUDA runtime error, text in dmel_last_error() */
 #define DMEL_ERR_NO_DEVICE (-4)   /* no CUDA device: there is no CPU fallback */
+
+#define DMEL_DTYPE_F32 0
+#define DMEL_DTYPE_BF16 1
 
 typedef struct dmel_plan dmel_plan;
 typedef struct dmel_stream dmel_stream;
@@ -68,6 +71,16 @@ long long dmel_plan_num_frames(const dmel_plan* plan, long long n_samples);
  * (reference dmel_codec/utils/spectrogram.py:41-81). */
 int dmel_logmel_f32(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
                     long long row_stride, float* logmel_dev, void* stream);
+
+/* waveform -> masked log-mel in the encoder's dtype, one launch.  Frames at or past
+ * lengths[b] / hop are written as 0 and never computed; out_dev is (B, n_mels, T) float32
+ * (DMEL_DTYPE_F32) or bfloat16 (DMEL_DTYPE_BF16, round-to-nearest-even of the float32 value).
+ * lengths_dev NULL = no masking.  Replaces the transform + cast + sequence_mask multiply of
+ * VQGAN.encode_unquantized (reference models/codec_lit_modules.py:486-507, mask rule
+ * utils/utils.py:48-55); the caller's (B*G, n_mels/G, T) group view of the result is free. */
+int dmel_logmel_masked(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
+                       long long row_stride, const int32_t* lengths_dev, int out_dtype,
+                       void* out_dev, void* stream);
 
 /* Calibration pass: running per-channel min / max of the log-mel of this batch
  * over valid frames (t < lengths[b] / hop; lengths_dev may be NULL = all T).

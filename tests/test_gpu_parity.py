@@ -366,3 +366,27 @@ def test_streaming_host_chunks_and_errors(d):
         enc.push(torch.zeros(3, 10))  # wrong number of streams
     with pytest.raises(ValueError):
         enc.push(torch.zeros(2, 1 << 20))  # does not fit the history buffer
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_masked_logmel_matches_call_site(d, dtype):
+    """LogMelSpectrogram.masked == transform -> .to(dtype) -> * sequence_mask of the reference's
+    VQGAN.encode_unquantized (models/codec_lit_modules.py:486-507), in one launch."""
+    from dmel_codec_b200 import synth
+    kw = GOLDEN_GEOMETRY["cfg2_24k_128"]
+    n = 24000 * 2 + 300
+    wav = synth.batch(range(720, 725), n, 24000, "speech").cuda()
+    lengths = torch.tensor([n, n - 1, 24000, 700, 0], dtype=torch.int64, device="cuda")
+    mt = d.LogMelSpectrogram(**kw).cuda()
+    full = mt(wav)                                   # (B, M, T) float32, every frame
+    mels, mel_lengths = mt.masked(wav, lengths, dtype)
+    assert mels.dtype == dtype and mels.shape == full.shape
+    assert torch.equal(mel_lengths, lengths // kw["hop_length"])
+    mask = (torch.arange(full.shape[2], device="cuda")[None, :] < mel_lengths[:, None])[:, None, :]
+    want = full.to(dtype) * mask.to(dtype)
+    assert torch.equal(mels, want)                   # same bits (0 == -0 under torch.equal)
+    # the group view the caller takes is a view, not a copy
+    g = 8
+    assert mels.view(mels.shape[0] * g, mels.shape[1] // g, mels.shape[2]).data_ptr() == mels.data_ptr()
+    # no lengths: plain cast
+    assert torch.equal(mt.spectrogram.plan_for(wav.device).logmel_masked(wav, None, dtype), full.to(dtype))
