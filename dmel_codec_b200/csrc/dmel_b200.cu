@@ -2,6 +2,7 @@
 // Host side: plan construction (banded filterbank, twiddle tables), argument
 // checking, kernel launches.  No torch, no cuFFT, no CPU fallback.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -67,6 +68,10 @@ struct dmel_plan {
   float2* d_fold_tw = nullptr;
   int2* d_chan = nullptr;
   float* d_weights = nullptr;
+  // dynamic tile scheduling: kSchedSlots {next tile, finished CTAs} pairs, zero between launches; launches rotate
+  // through them so that launches of one plan that overlap on different streams do not share a counter
+  int* d_sched = nullptr;
+  mutable std::atomic<unsigned> sched_turn{0};
   // scratch for the host-buffer entry point (grown on demand)
   cudaStream_t streams[2] = {nullptr, nullptr};
   float* d_wav[2] = {nullptr, nullptr};
@@ -99,6 +104,8 @@ auto dispatch_variant(int n_fft, int tf, int occ, F&& f) {
   if (tf == 8 && occ == 2) return f.template operator()<2048, 8, 2>();
   return tf == 16 ? f.template operator()<2048, 16, 1>() : f.template operator()<2048, 8, 1>();
 }
+
+constexpr unsigned kSchedSlots = 64;
 
 struct FillOffsets {
   FusedParams* p;
@@ -270,6 +277,7 @@ int prepare_window(dmel_plan* plan, const float* wav, long long n_rows, long lon
   p->weights = plan->d_weights;
   p->n_bins = 1;
   p->kmax = 0.f;
+  if (plan->d_sched && !std::getenv("DMEL_STATIC_TILES")) p->sched = plan->d_sched + 2 * (plan->sched_turn++ % kSchedSlots);
   if (const char* dbg = std::getenv("DMEL_DEBUG_SKIP")) p->debug_skip = std::atoi(dbg);  // ablation timing only
   dispatch_variant(plan->n_fft, plan->tile_frames, plan->ctas_per_sm, FillOffsets{p});
   *grid = (int)std::max<long long>(1, std::min<long long>(n_tiles, (long long)plan->sm_count * plan->ctas_per_sm));
@@ -397,6 +405,7 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
   if (e == cudaSuccess) e = upload(&plan->d_fold_tw, fold_tw);
   if (e == cudaSuccess) e = upload(&plan->d_chan, chan);
   if (e == cudaSuccess) e = upload(&plan->d_weights, weights);
+  if (e == cudaSuccess) e = upload(&plan->d_sched, std::vector<int>(2 * kSchedSlots, 0));
   if (e != cudaSuccess) {
     dmel_plan_destroy(plan);
     return fail(DMEL_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(e));
@@ -413,6 +422,7 @@ void dmel_plan_destroy(dmel_plan* plan) {
   cudaFree(plan->d_fold_tw);
   cudaFree(plan->d_chan);
   cudaFree(plan->d_weights);
+  cudaFree(plan->d_sched);
   for (int i = 0; i < 2; ++i) {
     cudaFree(plan->d_wav[i]);
     cudaFree(plan->d_codes[i]);

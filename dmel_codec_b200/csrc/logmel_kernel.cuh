@@ -69,6 +69,7 @@ struct FusedParams {
   // byte offsets of the shared-memory regions (FusedLayout, filled in by the host so the kernel
   // does no layout arithmetic)
   int off_mags, off_wave, off_window, off_fold, off_chan, off_weights, off_perchan, off_bars;
+  int* sched;               // {next dynamic tile, finished CTAs}, both 0 between launches; null = static tile walk
   int debug_skip;           // diagnostics (env DMEL_DEBUG_SKIP): 1 skip the FFT phase, 2 skip mel/epilogue, 4 skip staging
   float* run_min;           // (M) running min, updated in place [kOutStats]
   float* run_max;           // (M)
@@ -168,7 +169,7 @@ struct FusedLayout {
     return align16(perchan_off(wave_len, n_chan, nnz) + size_t(n_chan) * 8);  // {lo, scale} or {min, max}
   }
   static __host__ __device__ size_t total(int wave_len, int n_chan, int nnz) {
-    return bar_off(wave_len, n_chan, nnz) + 16;
+    return bar_off(wave_len, n_chan, nnz) + 32;  // two mbarriers + the next-tile slot
   }
 };
 
@@ -224,26 +225,6 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   const int warp = tid >> 5;
   float2* my_tile = tiles + warp * LY::kTileF2;
 
-  // ---- per-CTA constants -------------------------------------------------
-  for (int i = tid; i < p.n_chan_pad; i += kThreads) {
-    s_chan[i] = p.chan[i];
-    if constexpr (kCodes) {
-      const bool real = i < p.n_mels;
-      s_lo[i] = real ? p.q_lo[i] : 0.f;
-      s_scale[i] = real ? p.q_scale[i] : 0.f;
-    } else {
-      s_min[i] = __int_as_float(0x7f800000);
-      s_max[i] = __int_as_float(0xff800000);
-    }
-  }
-  for (int i = tid; i < p.nnz; i += kThreads) s_weights[i] = p.weights[i];
-  for (int i = tid; i < LY::kMagFloats; i += kThreads) mags[i] = 0.f;  // the 3 pad columns of each row stay zero
-  if constexpr (LY::kWindowInSmem) {
-    for (int i = tid; i < NFFT; i += kThreads) s_window[i] = p.window[i];
-  }
-  if constexpr (NFFT == 2048 && !kSplit) {
-    for (int i = tid; i < LY::kFoldN; i += kThreads) s_fold[i] = p.fold_tw[i];
-  }
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -336,12 +317,45 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
     }
   };
 
-  __syncthreads();  // constants + barrier init visible
+  // The first tile's samples leave HBM before anything else; the per-CTA constants (L2 resident after
+  // the first CTAs) are fetched while that copy is in flight.
   int tile = blockIdx.x;
   TileInfo cur = describe(tile < p.n_tiles ? tile : 0);
+#ifndef DMEL_LATE_FIRST_STAGE
   if (tile < p.n_tiles) stage(cur, 0);
+#endif
 
-  for (int it = 0; tile < p.n_tiles; tile += gridDim.x, ++it) {
+  // ---- per-CTA constants -------------------------------------------------
+  for (int i = tid; i < p.n_chan_pad; i += kThreads) {
+    s_chan[i] = p.chan[i];
+    if constexpr (kCodes) {
+      const bool real = i < p.n_mels;
+      s_lo[i] = real ? p.q_lo[i] : 0.f;
+      s_scale[i] = real ? p.q_scale[i] : 0.f;
+    } else {
+      s_min[i] = __int_as_float(0x7f800000);
+      s_max[i] = __int_as_float(0xff800000);
+    }
+  }
+  for (int i = tid; i < p.nnz; i += kThreads) s_weights[i] = p.weights[i];
+  for (int i = tid; i < LY::kMagFloats; i += kThreads) mags[i] = 0.f;  // the 3 pad columns of each row stay zero
+  if constexpr (LY::kWindowInSmem) {
+    for (int i = tid; i < NFFT; i += kThreads) s_window[i] = p.window[i];
+  }
+  if constexpr (NFFT == 2048 && !kSplit) {
+    for (int i = tid; i < LY::kFoldN; i += kThreads) s_fold[i] = p.fold_tw[i];
+  }
+  __syncthreads();  // constants + barrier init visible
+#ifdef DMEL_LATE_FIRST_STAGE
+  if (tile < p.n_tiles) stage(cur, 0);
+#endif
+  // Tiles after the first are handed out by a global counter (lean variants), so the CTAs of the
+  // grid finish within one tile of each other instead of one or two tiles apart.
+  constexpr bool kDynamic = LY::kWaveBufs == 1;
+  int* s_next = reinterpret_cast<int*>(bars + 2);
+  const bool dynamic = kDynamic && p.sched != nullptr;
+
+  for (int it = 0; tile < p.n_tiles; ++it) {
     const int b = LY::kWaveBufs == 2 ? (it & 1) : 0;
     const float* wave = wave0 + b * p.wave_len;
     const bool dead = cur.frame_limit == 0;
@@ -354,10 +368,16 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
       }
       if (cur.manual) __syncthreads();  // plain stores of all threads
     }
-    const bool has_next = tile + (int)gridDim.x < p.n_tiles;
-    const TileInfo nxt = describe(has_next ? tile + (int)gridDim.x : tile);
-    if constexpr (LY::kWaveBufs == 2) {
-      if (has_next) stage(nxt, b ^ 1);  // double buffered: the next tile loads while this one computes
+    int next_tile = tile + (int)gridDim.x;
+    int fetched = 0;
+    if (dynamic && tid == 0) fetched = atomicAdd(p.sched, 1);  // consumed just before the barrier below
+    bool has_next = next_tile < p.n_tiles;
+    TileInfo nxt = cur;
+    if constexpr (!kDynamic) {
+      nxt = describe(has_next ? next_tile : tile);
+      if constexpr (LY::kWaveBufs == 2) {
+        if (has_next) stage(nxt, b ^ 1);  // double buffered: the next tile loads while this one computes
+      }
     }
 
     // ---- 2. FFT -> magnitudes ------------------------------------------------
@@ -485,7 +505,15 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
         }
       }
     }
+    if constexpr (kDynamic) {
+      if (dynamic && tid == 0) *s_next = (int)gridDim.x + fetched;
+    }
     __syncthreads();
+    if constexpr (kDynamic) {
+      if (dynamic) next_tile = *s_next;
+      has_next = next_tile < p.n_tiles;
+      nxt = describe(has_next ? next_tile : tile);
+    }
     if constexpr (LY::kWaveBufs == 1) {
       if (has_next) stage(nxt, 0);  // single buffer: it is free now, the copy flies under the mel phase
     }
@@ -570,6 +598,17 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
     }
     __syncthreads();  // mags and wave[b] are free again
     cur = nxt;
+    tile = next_tile;
+  }
+  if constexpr (kDynamic) {
+    // the last CTA to finish leaves both counters at zero for the next launch
+    if (dynamic && tid == 0) {
+      __threadfence();
+      if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+        atomicExch(p.sched, 0);
+        atomicExch(p.sched + 1, 0);
+      }
+    }
   }
 
   // ---- flush per-CTA statistics -------------------------------------------

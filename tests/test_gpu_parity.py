@@ -390,3 +390,22 @@ def test_masked_logmel_matches_call_site(d, dtype):
     assert mels.view(mels.shape[0] * g, mels.shape[1] // g, mels.shape[2]).data_ptr() == mels.data_ptr()
     # no lengths: plain cast
     assert torch.equal(mt.spectrogram.plan_for(wav.device).logmel_masked(wav, None, dtype), full.to(dtype))
+
+
+def test_dynamic_tile_schedule_matches_static(d, monkeypatch):
+    """Tiles handed out by the global counter give the same bytes as the static walk, launch after
+    launch (the counter pair of a launch must be back at zero when its slot comes round again)."""
+    from dmel_codec_b200 import synth
+    kw = GOLDEN_GEOMETRY["cfg2_24k_128"]
+    wav = synth.device_batch(range(40), 24000 * 4 + 77, 24000, "cuda")
+    lengths = torch.randint(1000, wav.shape[-1], (40,), generator=torch.Generator().manual_seed(5)).to("cuda", torch.int32)
+    tok = _tokenizer(d, kw, 16)
+    tok.calibrate([wav])
+    monkeypatch.setenv("DMEL_STATIC_TILES", "1")
+    want, _ = tok.encode(wav, lengths)
+    want_mel = tok.mel_transform(wav)
+    monkeypatch.delenv("DMEL_STATIC_TILES")
+    for _ in range(70):  # more launches than counter slots
+        got, _ = tok.encode(wav, lengths)
+        assert torch.equal(got, want)
+    assert torch.equal(tok.mel_transform(wav), want_mel)
