@@ -242,7 +242,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # CPU baseline: the oracle port on this box's host cores, bounded sample
     cores = os.cpu_count() or 1
     cpu_value, passes, cpu_dt = None, 0, 0.0
-    if not args.skip_cpu:
+    if not args.skip_cpu and world == 1:  # the CPU baseline is a 1-GPU-run line (rank 0, N = 1 only)
         torch.set_num_threads(cores)
         cwav, cfg, bank, clo, chi = cpu_oracle_setup(BATCH)
         oracle_step(cwav, cfg, bank, clo, chi)
