@@ -210,7 +210,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     # ---- end to end through the public API with HOST buffers -------------------
     e2e_steps = max(3, min(args.steps, 10))
-    e2e_value = None
+    e2e_value = e2e_pcm_value = None
     if not args.skip_e2e:
         host = [ring[r].cpu().pin_memory() for r in range(2)]
         out = torch.empty((BATCH, GEOM["n_mels"], N_FRAMES), dtype=torch.uint8).pin_memory()
@@ -226,6 +226,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         if world > 1:
             dist.all_reduce(e, op=dist.ReduceOp.MAX)
         e2e_value = world * AUDIO_SEC_PER_BATCH * e2e_steps / e.item()
+        # the same call with the waveform as int16 PCM (the format audio is stored in): half the H2D bytes
+        host_pcm = [(h.clamp(-1, 1) * 32767.0).round().to(torch.int16).pin_memory() for h in host]
+        for r in range(2):
+            tok.encode_host(host_pcm[r], out=out)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            tok.encode_host(host_pcm[i % 2], out=out)
+        e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e, op=dist.ReduceOp.MAX)
+        e2e_pcm_value = world * AUDIO_SEC_PER_BATCH * e2e_steps / e.item()
 
     if rank != 0:
         return
@@ -272,6 +285,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * BATCH * N_SAMPLES,
                 "d2h_bytes_per_step": BATCH * GEOM["n_mels"] * N_FRAMES, "steps": e2e_steps,
                 "call": "DMelTokenizer.encode_host -> dmel_encode_host_u8 (pinned host wav in, host codes out)"},
+        "e2e_pcm16": {"value": e2e_pcm_value, "unit": UNIT, "h2d_bytes_per_step": 2 * BATCH * N_SAMPLES,
+                      "d2h_bytes_per_step": BATCH * GEOM["n_mels"] * N_FRAMES, "steps": e2e_steps,
+                      "call": "same call with int16 PCM host waveforms (dmel_encode_host_pcm16_u8); secondary line, "
+                              "the reference interface takes float32"},
         "gpu_launches": 2 * args.steps,
         "clocks": clocks.summary(),
     }))

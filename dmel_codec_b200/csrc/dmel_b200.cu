@@ -62,8 +62,9 @@ struct dmel_plan {
   int nnz = 0;
   int n_chan_pad = 0;  // n_mels rounded up to the channel-group size 32 / tile_frames
   size_t smem_bytes = 0;
-  mutable unsigned smem_opt_in = 0;  // bit per output MODE whose kernel already has its dynamic-smem limit raised
+  mutable unsigned long long smem_opt_in = 0;  // bit per output MODE whose kernel already has its dynamic-smem limit raised
   float* d_window = nullptr;
+  float* d_window_pcm = nullptr;  // window / 32768: int16 PCM input needs no separate scaling pass
   float2* d_stage_tw = nullptr;
   float2* d_fold_tw = nullptr;
   int2* d_chan = nullptr;
@@ -140,11 +141,20 @@ struct Launch {
   cudaStream_t st;
   template <int NFFT, int TF, int OCC>
   cudaError_t operator()() const {
+    constexpr bool kLeanVariant = OCC == 3 || (NFFT == 2048 && OCC == 2);
+    if constexpr ((MODE & dmel::kInPcm16) != 0 && !kLeanVariant) {
+      return cudaErrorNotSupported;  // int16 input is built for the register-lean variants only
+    } else {
+      return launch<NFFT, TF, OCC>();
+    }
+  }
+  template <int NFFT, int TF, int OCC>
+  cudaError_t launch() const {
     auto kern = dmel::dmel_fused_kernel<NFFT, TF, MODE, OCC>;
-    if (!(plan->smem_opt_in & (1u << MODE))) {  // once per plan and output mode
+    if (!(plan->smem_opt_in & (1ull << MODE))) {  // once per plan and output mode
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
       if (e != cudaSuccess) return e;
-      plan->smem_opt_in |= 1u << MODE;
+      plan->smem_opt_in |= 1ull << MODE;
     }
     kern<<<grid, dmel::kThreads, plan->smem_bytes, st>>>(*p);
     return cudaGetLastError();
@@ -157,7 +167,7 @@ cudaError_t launch_fused_mode(const dmel_plan* plan, const FusedParams& p, int g
 }
 
 cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st,
-                             bool bf16_logmel = false) {
+                             bool bf16_logmel = false, bool pcm16 = false) {
   using namespace dmel;
   int mode = 0;
   if (p.codes) mode |= kOutCodes;
@@ -165,8 +175,10 @@ cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int gr
   if (p.run_min) mode |= kOutStats;
   if (p.near_edge) mode |= kOutEdge;
   if (bf16_logmel) mode |= kOutBf16;
+  if (pcm16) mode |= kInPcm16;
   switch (mode) {
     case kOutCodes: return launch_fused_mode<kOutCodes>(plan, p, grid, st);
+    case kOutCodes | kInPcm16: return launch_fused_mode<kOutCodes | kInPcm16>(plan, p, grid, st);
     case kOutLogmel: return launch_fused_mode<kOutLogmel>(plan, p, grid, st);
     case kOutLogmel | kOutBf16: return launch_fused_mode<kOutLogmel | kOutBf16>(plan, p, grid, st);
     case kOutStats: return launch_fused_mode<kOutStats>(plan, p, grid, st);
@@ -367,7 +379,7 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
   for (const Variant& v : kVariants) {
     if (v.n_fft != n_fft || (occ_pin && v.occ != occ_pin)) continue;
     band_filterbank(mel_basis_host, n_mels, n_fft / 2 + 1, 32 / v.tf, &chan, &weights);
-    const int wave_len = ((v.tf - 1) * hop_length + n_fft + 3) / 4 * 4;
+    const int wave_len = ((v.tf - 1) * hop_length + n_fft + 7) / 8 * 8;  // whole 16-byte units of float and of int16
     const size_t need = dispatch_variant(v.n_fft, v.tf, v.occ, SmemNeed{wave_len, (int)chan.size(), (int)weights.size()});
     const size_t limit = std::min<size_t>((size_t)max_sm_smem / v.occ - 1024, (size_t)plan->max_smem);  // 1 KB/CTA reserved
     if (need <= limit) {
@@ -400,7 +412,10 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
     const double a = -two_pi * double(k) / n_fft;
     fold_tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
   }
+  std::vector<float> window_pcm(window);
+  for (float& w : window_pcm) w *= 1.0f / 32768.0f;  // exact: a power of two
   cudaError_t e = upload(&plan->d_window, window);
+  if (e == cudaSuccess) e = upload(&plan->d_window_pcm, window_pcm);
   if (e == cudaSuccess) e = upload(&plan->d_stage_tw, stage_tw);
   if (e == cudaSuccess) e = upload(&plan->d_fold_tw, fold_tw);
   if (e == cudaSuccess) e = upload(&plan->d_chan, chan);
@@ -418,6 +433,7 @@ void dmel_plan_destroy(dmel_plan* plan) {
   if (!plan) return;
   DeviceGuard guard(plan->device);
   cudaFree(plan->d_window);
+  cudaFree(plan->d_window_pcm);
   cudaFree(plan->d_stage_tw);
   cudaFree(plan->d_fold_tw);
   cudaFree(plan->d_chan);
@@ -521,6 +537,30 @@ int dmel_encode_u8(dmel_plan* plan, const float* wav_dev, long long n_rows, long
   p.edge_eps = edge_eps;
   DeviceGuard guard(plan->device);
   DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream));
+  return DMEL_OK;
+}
+
+int dmel_encode_pcm16_u8(dmel_plan* plan, const int16_t* wav_dev, long long n_rows, long long n_samples,
+                         long long row_stride, const int32_t* lengths_dev, const float* lo_dev,
+                         const float* scale_dev, int n_bins, uint8_t* codes_dev, void* stream) {
+  FusedParams p;
+  int grid = 0;
+  int rc = prepare_fused(plan, reinterpret_cast<const float*>(wav_dev), n_rows, n_samples, row_stride, &p, &grid);
+  if (rc != DMEL_OK) return rc;
+  if ((rc = check_bins(n_bins)) != DMEL_OK) return rc;
+  if (!lo_dev || !scale_dev || !codes_dev) return fail(DMEL_ERR_INVALID, "lo_dev / scale_dev / codes_dev is null");
+  if (!(plan->ctas_per_sm == 3 || (plan->n_fft == 2048 && plan->ctas_per_sm == 2)))
+    return fail(DMEL_ERR_UNSUPPORTED, "int16 input needs the register-lean kernel variant, which does not fit this geometry");
+  if (n_rows == 0) return DMEL_OK;
+  p.window = plan->d_window_pcm;
+  p.lengths = lengths_dev;
+  p.q_lo = lo_dev;
+  p.q_scale = scale_dev;
+  p.n_bins = n_bins;
+  p.kmax = float(n_bins - 1);
+  p.codes = codes_dev;
+  DeviceGuard guard(plan->device);
+  DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream, false, true));
   return DMEL_OK;
 }
 
@@ -689,10 +729,11 @@ int dmel_stream_flush(dmel_stream* s, const float* lo_dev, const float* scale_de
   return rc;
 }
 
-int dmel_encode_host_u8(dmel_plan* plan, const float* wav_host, long long n_rows, long long n_samples,
+static int encode_host_impl(dmel_plan* plan, const void* wav_host_v, int elem, long long n_rows, long long n_samples,
                         long long row_stride, const int32_t* lengths_host, const float* lo_host,
                         const float* scale_host, int n_bins, uint8_t* codes_host) {
   if (!plan) return fail(DMEL_ERR_INVALID, "plan is null");
+  const char* wav_host = static_cast<const char*>(wav_host_v);
   if (!wav_host || !codes_host || !lo_host || !scale_host)
     return fail(DMEL_ERR_INVALID, "wav_host / codes_host / lo_host / scale_host is null");
   int rc = check_bins(n_bins);
@@ -714,7 +755,7 @@ int dmel_encode_host_u8(dmel_plan* plan, const float* wav_host, long long n_rows
   }
   // rows per chunk: a few MiB of waveform (DMEL_HOST_CHUNK_MB, default 16), so copies and kernels of
   // neighbouring chunks overlap and the un-overlapped tail (last kernel + last D2H) stays short
-  const long long row_bytes = n_samples * 4;
+  const long long row_bytes = n_samples * elem;
   long long chunk_mb = 16;
   if (const char* env = std::getenv("DMEL_HOST_CHUNK_MB")) chunk_mb = std::max(1, std::atoi(env));
   long long chunk_rows = std::max<long long>(1, (chunk_mb << 20) / row_bytes);
@@ -725,7 +766,7 @@ int dmel_encode_host_u8(dmel_plan* plan, const float* wav_host, long long n_rows
     for (int i = 0; i < 2; ++i) {
       cudaFree(plan->d_wav[i]);
       plan->d_wav[i] = nullptr;
-      DMEL_CUDA(cudaMalloc((void**)&plan->d_wav[i], wav_need * sizeof(float)));
+      DMEL_CUDA(cudaMalloc((void**)&plan->d_wav[i], wav_need * sizeof(float)));  // sized for float, int16 uses half
     }
     plan->wav_cap = wav_need;
   }
@@ -754,18 +795,20 @@ int dmel_encode_host_u8(dmel_plan* plan, const float* wav_host, long long n_rows
     cudaStream_t st = plan->streams[slot];
     // stream order already guarantees the slot's previous D2H finished before this H2D starts
     if (row_stride == n_samples)
-      DMEL_CUDA(cudaMemcpyAsync(plan->d_wav[slot], wav_host + r0 * row_stride, (size_t)rows * n_samples * 4,
+      DMEL_CUDA(cudaMemcpyAsync(plan->d_wav[slot], wav_host + r0 * row_stride * elem, (size_t)rows * n_samples * elem,
                                 cudaMemcpyHostToDevice, st));
     else
-      DMEL_CUDA(cudaMemcpy2DAsync(plan->d_wav[slot], n_samples * 4, wav_host + r0 * row_stride, row_stride * 4,
-                                  n_samples * 4, rows, cudaMemcpyHostToDevice, st));
+      DMEL_CUDA(cudaMemcpy2DAsync(plan->d_wav[slot], n_samples * elem, wav_host + r0 * row_stride * elem, row_stride * elem,
+                                  n_samples * elem, rows, cudaMemcpyHostToDevice, st));
     const int32_t* len_dev = nullptr;
     if (lengths_host) {
       DMEL_CUDA(cudaMemcpyAsync(plan->d_len[slot], lengths_host + r0, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
       len_dev = plan->d_len[slot];
     }
-    rc = dmel_encode_u8(plan, plan->d_wav[slot], rows, n_samples, n_samples, len_dev, plan->d_lo, plan->d_scale,
-                        n_bins, plan->d_codes[slot], nullptr, nullptr, 0.f, st);
+    rc = elem == 2 ? dmel_encode_pcm16_u8(plan, reinterpret_cast<const int16_t*>(plan->d_wav[slot]), rows, n_samples, n_samples,
+                                          len_dev, plan->d_lo, plan->d_scale, n_bins, plan->d_codes[slot], st)
+                   : dmel_encode_u8(plan, plan->d_wav[slot], rows, n_samples, n_samples, len_dev, plan->d_lo, plan->d_scale,
+                                    n_bins, plan->d_codes[slot], nullptr, nullptr, 0.f, st);
     if (rc != DMEL_OK) return rc;
     DMEL_CUDA(cudaMemcpyAsync(codes_host + (size_t)r0 * plan->n_mels * T, plan->d_codes[slot],
                               (size_t)rows * plan->n_mels * T, cudaMemcpyDeviceToHost, st));
@@ -773,6 +816,18 @@ int dmel_encode_host_u8(dmel_plan* plan, const float* wav_host, long long n_rows
   DMEL_CUDA(cudaStreamSynchronize(plan->streams[0]));
   DMEL_CUDA(cudaStreamSynchronize(plan->streams[1]));
   return DMEL_OK;
+}
+
+int dmel_encode_host_u8(dmel_plan* plan, const float* wav_host, long long n_rows, long long n_samples,
+                        long long row_stride, const int32_t* lengths_host, const float* lo_host,
+                        const float* scale_host, int n_bins, uint8_t* codes_host) {
+  return encode_host_impl(plan, wav_host, 4, n_rows, n_samples, row_stride, lengths_host, lo_host, scale_host, n_bins, codes_host);
+}
+
+int dmel_encode_host_pcm16_u8(dmel_plan* plan, const int16_t* wav_host, long long n_rows, long long n_samples,
+                              long long row_stride, const int32_t* lengths_host, const float* lo_host,
+                              const float* scale_host, int n_bins, uint8_t* codes_host) {
+  return encode_host_impl(plan, wav_host, 2, n_rows, n_samples, row_stride, lengths_host, lo_host, scale_host, n_bins, codes_host);
 }
 
 static int check_tensor(const void* a, const void* b, long long n_rows, int n_mels, long long n_frames,

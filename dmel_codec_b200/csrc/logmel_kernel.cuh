@@ -18,6 +18,7 @@
 // out; constants come from L2.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -35,9 +36,10 @@ constexpr int kOutLogmel = 2;
 constexpr int kOutStats = 4;
 constexpr int kOutEdge = 8;  // count values within edge_eps of an interior bin edge (needs kOutCodes)
 constexpr int kOutBf16 = 16;  // the log-mel output tensor is bfloat16 (needs kOutLogmel)
+constexpr int kInPcm16 = 32;  // the waveform is int16 PCM (x / 32768 is folded into the window taps); lean variants only
 
 struct FusedParams {
-  const float* wav;         // (B, row_stride) device
+  const float* wav;         // (B, row_stride) device; int16_t with kInPcm16
   long long row_stride;     // samples between rows
   int n_rows;               // B
   int n_samples;            // L: length of the (virtual) row the reflect padding refers to
@@ -197,6 +199,11 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   constexpr bool kCodes = (MODE & kOutCodes) != 0, kLogmel = (MODE & kOutLogmel) != 0;
   constexpr bool kStats = (MODE & kOutStats) != 0, kEdge = (MODE & kOutEdge) != 0;
   constexpr bool kBf16 = (MODE & kOutBf16) != 0;
+  constexpr bool kPcm = (MODE & kInPcm16) != 0;
+  static_assert(!kPcm || kLean, "int16 input is built for the register-lean variants");
+  using wave_t = std::conditional_t<kPcm, short, float>;
+  constexpr int kAlign = 16 / (int)sizeof(wave_t);  // samples per 16 bytes: granularity of the bulk copies
+  const wave_t* wav = reinterpret_cast<const wave_t*>(p.wav);
   static_assert(!kBf16 || kLogmel, "kOutBf16 qualifies the log-mel output");
   auto store_logmel = [&](size_t o, float v) {
     if constexpr (kBf16) reinterpret_cast<__nv_bfloat16*>(p.logmel)[o] = __float2bfloat16_rn(v);
@@ -206,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   extern __shared__ __align__(16) unsigned char smem[];
   float2* tiles = reinterpret_cast<float2*>(smem);
   float* mags = reinterpret_cast<float*>(smem + p.off_mags);
-  float* wave0 = reinterpret_cast<float*>(smem + p.off_wave);
+  wave_t* wave0 = reinterpret_cast<wave_t*>(smem + p.off_wave);
   float* s_window = reinterpret_cast<float*>(smem + p.off_window);
   float2* s_fold = reinterpret_cast<float2*>(smem + p.off_fold);
   int2* s_chan = reinterpret_cast<int2*>(smem + p.off_chan);
@@ -265,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
 
   const int padded_len = p.n_samples + 2 * p.pad_inner + 2 * p.pad_outer;
   const bool hop_even = (p.hop & 1) == 0;
-  const bool row_vec_ok = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0) && ((p.row_stride & 3) == 0);
+  const bool row_vec_ok = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0) && ((p.row_stride & (kAlign - 1)) == 0);
   unsigned long long edge_hits = 0;
   uint32_t phase_bits = 0;  // bit b: parity to wait for on bars[b]
 
@@ -284,10 +291,11 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
     const int s0 = (p.t_begin + ti.t0) * p.hop - p.pad_inner - p.pad_outer;  // virtual sample under the tile's first tap
     const int b0 = s0 - p.src_base;                                          // where that sample sits in the buffer
     ti.src0 = (long long)ti.row * p.row_stride + b0;
-    int lo = s0 < 0 ? ((-s0 + 3) & ~3) : 0;                                   // first wave index with a real sample
-    if (b0 + lo < 0) lo = (-b0 + 3) & ~3;                                     // ... that is resident in the buffer
-    int hi = p.n_samples - s0 < p.wave_len ? ((p.n_samples - s0) & ~3) : p.wave_len;  // one past the last
-    const bool can_bulk = row_vec_ok && p.pad_outer == 0 && (b0 & 3) == 0 && hi > lo;
+    constexpr int kA = kAlign - 1;
+    int lo = s0 < 0 ? ((-s0 + kA) & ~kA) : 0;                                 // first wave index with a real sample
+    if (b0 + lo < 0) lo = (-b0 + kA) & ~kA;                                   // ... that is resident in the buffer
+    int hi = p.n_samples - s0 < p.wave_len ? ((p.n_samples - s0) & ~kA) : p.wave_len;  // one past the last
+    const bool can_bulk = row_vec_ok && p.pad_outer == 0 && (b0 & kA) == 0 && hi > lo;
     ti.bulk_lo = can_bulk ? lo : 0;
     ti.bulk_n = can_bulk ? hi - lo : 0;
     ti.manual = !can_bulk || lo > 0 || hi < p.wave_len;
@@ -296,21 +304,21 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   // Start filling wave buffer b with the samples of a tile.
   auto stage = [&](const TileInfo& ti, int b) {
     if (ti.frame_limit == 0 || (p.debug_skip & 4)) return;
-    float* wave = wave0 + b * p.wave_len;
+    wave_t* wave = wave0 + b * p.wave_len;
     if (ti.bulk_n && tid == 0) {
       fence_proxy_async();  // earlier generic-proxy reads of this buffer are ordered before the async write
-      mbar_expect_tx(&bars[b], ti.bulk_n * 4);
-      bulk_copy_g2s(wave + ti.bulk_lo, p.wav + ti.src0 + ti.bulk_lo, ti.bulk_n * 4, &bars[b]);
+      mbar_expect_tx(&bars[b], ti.bulk_n * (int)sizeof(wave_t));
+      bulk_copy_g2s(wave + ti.bulk_lo, wav + ti.src0 + ti.bulk_lo, ti.bulk_n * (int)sizeof(wave_t), &bars[b]);
     }
     if (ti.manual) {
-      const float* src = p.wav + (long long)ti.row * p.row_stride - p.src_base;
+      const wave_t* src = wav + (long long)ti.row * p.row_stride - p.src_base;
       const int j0 = (p.t_begin + ti.t0) * p.hop;  // first position in the padded row
       const int skip_lo = ti.bulk_lo, skip_hi = ti.bulk_lo + ti.bulk_n;
       const int n_manual = p.wave_len - ti.bulk_n;
       for (int q = tid; q < n_manual; q += kThreads) {
         const int i = q < skip_lo ? q : q + (skip_hi - skip_lo);  // wave index outside the bulk range
         const int j = j0 + i;
-        float x = 0.f;
+        wave_t x = 0;
         if (j < padded_len) x = __ldg(src + reflect_src(j, p.n_samples, p.pad_inner, p.pad_outer));
         wave[i] = x;
       }
@@ -357,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
 
   for (int it = 0; tile < p.n_tiles; ++it) {
     const int b = LY::kWaveBufs == 2 ? (it & 1) : 0;
-    const float* wave = wave0 + b * p.wave_len;
+    const wave_t* wave = wave0 + b * p.wave_len;
     const bool dead = cur.frame_limit == 0;
 
     // ---- 1. this tile's samples are in wave[b]; start fetching the next tile
@@ -387,21 +395,25 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
       const int partner = mirror_lane512(lane);
 #pragma unroll 1
       for (int fr = warp; fr < fft_frames; fr += kWarps) {
-        const float* fa = wave + fr * p.hop;
+        const wave_t* fa = wave + fr * p.hop;
         float2 v[16];
         if (hop_even) {
-          const float2* f2 = reinterpret_cast<const float2*>(fa);
+          using pair_t = std::conditional_t<kPcm, short2, float2>;
+          const pair_t* f2 = reinterpret_cast<const pair_t*>(fa);
 #pragma unroll
           for (int n1 = 0; n1 < 16; ++n1) {
-            if constexpr (kLean) v[n1] = f2_mul(f2[32 * n1 + lane], my_win[32 * n1]);
-            else v[n1] = f2_mul(f2[32 * n1 + lane], win[n1]);
+            const pair_t x = f2[32 * n1 + lane];
+            const float2 xf = make_float2((float)x.x, (float)x.y);
+            if constexpr (kLean) v[n1] = f2_mul(xf, my_win[32 * n1]);
+            else v[n1] = f2_mul(xf, win[n1]);
           }
         } else {
 #pragma unroll
           for (int n1 = 0; n1 < 16; ++n1) {
             const int idx = 2 * (32 * n1 + lane);
-            if constexpr (kLean) v[n1] = f2_mul(make_float2(fa[idx], fa[idx + 1]), my_win[32 * n1]);
-            else v[n1] = f2_mul(make_float2(fa[idx], fa[idx + 1]), win[n1]);
+            const float2 xf = make_float2((float)fa[idx], (float)fa[idx + 1]);
+            if constexpr (kLean) v[n1] = f2_mul(xf, my_win[32 * n1]);
+            else v[n1] = f2_mul(xf, win[n1]);
           }
         }
         __syncwarp();  // previous frame's pass-2 reads of my_tile are done
@@ -446,23 +458,25 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
       const float4* win4 = reinterpret_cast<const float4*>(s_window) + lane;
 #pragma unroll 1
       for (int fr = warp; fr < fft_frames; fr += kWarps) {
-        const float* fa = wave + fr * p.hop;
+        const wave_t* fa = wave + fr * p.hop;
         float2 v[16], odd[16];  // even samples x[4n], x[4n+2] and odd samples x[4n+1], x[4n+3] of this lane
         if (hop_vec) {
-          const float4* f4 = reinterpret_cast<const float4*>(fa) + lane;
+          using quad_t = std::conditional_t<kPcm, short4, float4>;
+          const quad_t* f4 = reinterpret_cast<const quad_t*>(fa) + lane;
 #pragma unroll
           for (int n1 = 0; n1 < 16; ++n1) {
-            const float4 x = f4[32 * n1], w = win4[32 * n1];
-            v[n1] = make_float2(x.x * w.x, x.z * w.z);
-            odd[n1] = make_float2(x.y * w.y, x.w * w.w);
+            const quad_t x = f4[32 * n1];
+            const float4 w = win4[32 * n1];
+            v[n1] = make_float2((float)x.x * w.x, (float)x.z * w.z);
+            odd[n1] = make_float2((float)x.y * w.y, (float)x.w * w.w);
           }
         } else {
 #pragma unroll
           for (int n1 = 0; n1 < 16; ++n1) {
             const int idx = 4 * (32 * n1 + lane);
             const float4 w = win4[32 * n1];
-            v[n1] = make_float2(fa[idx] * w.x, fa[idx + 2] * w.z);
-            odd[n1] = make_float2(fa[idx + 1] * w.y, fa[idx + 3] * w.w);
+            v[n1] = make_float2((float)fa[idx] * w.x, (float)fa[idx + 2] * w.z);
+            odd[n1] = make_float2((float)fa[idx + 1] * w.y, (float)fa[idx + 3] * w.w);
           }
         }
         HalfSpectrum e, o;
@@ -473,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
     } else {
 #pragma unroll 1
       for (int fr = warp; fr < fft_frames; fr += kWarps) {
-        const float* fa = wave + fr * p.hop;
+        const float* fa = reinterpret_cast<const float*>(wave) + fr * p.hop;  // never int16: not a lean variant
         float2 v[32];
 #pragma unroll
         for (int n1 = 0; n1 < 32; ++n1) {

@@ -43,6 +43,21 @@ def as_rows(wav: torch.Tensor) -> torch.Tensor:
     return wav
 
 
+def as_pcm_rows(wav: torch.Tensor) -> torch.Tensor:
+    """(B, L) or (B, 1, L) int16 -> (B, L) int16 with unit stride along L."""
+    if wav.dtype != torch.int16:
+        raise ValueError(f"expected int16 PCM, got {wav.dtype}")
+    if wav.ndim == 3:
+        if wav.shape[1] != 1:
+            raise ValueError(f"expected mono audio (B, 1, L), got {tuple(wav.shape)}")
+        wav = wav[:, 0, :]
+    elif wav.ndim != 2:
+        raise ValueError(f"expected audio of shape (B, L) or (B, 1, L), got {tuple(wav.shape)}")
+    if wav.stride(1) != 1 or (wav.shape[0] > 1 and wav.stride(0) < wav.shape[1]):
+        wav = wav.contiguous()
+    return wav
+
+
 class Plan:
     def __init__(self, *, sample_rate: int, n_fft: int, win_length: int, hop_length: int, n_mels: int,
                  f_min: float = 0.0, f_max: Optional[float] = None, center: bool = False,
@@ -143,13 +158,28 @@ class Plan:
             _stream_ptr(rows.device)))
         return (codes, logmel) if return_logmel else codes
 
+    def encode_pcm16(self, wav: torch.Tensor, lengths: Optional[torch.Tensor], lo: torch.Tensor,
+                     scale: torch.Tensor, n_bins: int) -> torch.Tensor:
+        """int16 PCM (value = sample / 32768) -> codes; bit-identical to ``encode(wav.float() / 32768)``."""
+        _require_cuda(wav, "audio")
+        rows = as_pcm_rows(wav)
+        b, n = rows.shape
+        t = self._frames_or_raise(n)
+        codes = torch.empty((b, self.n_mels, t), dtype=torch.uint8, device=rows.device)
+        len_ptr = self._lengths_ptr(lengths, b, rows.device)
+        _native.check(_native.load().dmel_encode_pcm16_u8(
+            self._handle, rows.data_ptr(), b, n, rows.stride(0) if b > 1 else n, len_ptr[0],
+            lo.data_ptr(), scale.data_ptr(), int(n_bins), codes.data_ptr(), _stream_ptr(rows.device)))
+        return codes
+
     def encode_host(self, wav: torch.Tensor, lengths: Optional[torch.Tensor], lo: torch.Tensor,
                     scale: torch.Tensor, n_bins: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Host tensors in, host tensor out; copies and kernels are pipelined
         inside the library (``dmel_encode_host_u8``)."""
         if wav.is_cuda:
             raise ValueError("encode_host takes CPU tensors; use encode() for CUDA tensors")
-        rows = as_rows(wav)
+        pcm = wav.dtype == torch.int16  # int16 PCM: value = sample / 32768, half the bytes over PCIe
+        rows = as_pcm_rows(wav) if pcm else as_rows(wav)
         b, n = rows.shape
         t = self._frames_or_raise(n)
         if out is None:
@@ -162,7 +192,8 @@ class Plan:
             if len_h.numel() != b:
                 raise ValueError(f"lengths has {len_h.numel()} entries for a batch of {b}")
         with torch.cuda.device(self.device):
-            _native.check(_native.load().dmel_encode_host_u8(
+            fn = _native.load().dmel_encode_host_pcm16_u8 if pcm else _native.load().dmel_encode_host_u8
+            _native.check(fn(
                 self._handle, rows.data_ptr(), b, n, rows.stride(0) if b > 1 else n,
                 len_h.data_ptr() if len_h is not None else None, lo_h.data_ptr(), sc_h.data_ptr(),
                 int(n_bins), out.data_ptr()))

@@ -201,9 +201,21 @@ class DMelTokenizer(nn.Module):
         return out, code_lengths
 
     @torch.no_grad()
+    def encode_pcm16(self, audios: Tensor, audio_lengths: Optional[Tensor] = None):
+        """``encode`` for int16 PCM on the device (value = sample / 32768): same codes as
+        ``encode(audios.float() / 32768)``, half the waveform bytes.  -> (codes, code_lengths or None)."""
+        q = self.quantizer
+        q._check_ready()
+        lengths = self._flat_lengths(audio_lengths)
+        codes = self._plan(audios.device).encode_pcm16(audios, lengths, q.lo, q.scale(), q.n_bins)
+        code_lengths = None if lengths is None else torch.div(lengths, self.hop_length, rounding_mode="floor")
+        return codes, code_lengths
+
+    @torch.no_grad()
     def encode_host(self, audios: Tensor, audio_lengths: Optional[Tensor] = None,
                     out: Optional[Tensor] = None) -> Tensor:
-        """CPU (ideally pinned) waveforms in, CPU codes out, transfers pipelined natively."""
+        """CPU (ideally pinned) waveforms in, CPU codes out, transfers pipelined natively.
+        float32 waveforms, or int16 PCM (value = sample / 32768: half the PCIe bytes, same codes)."""
         q = self.quantizer
         q._check_ready()
         return self._plan(q.lo.device).encode_host(audios, self._flat_lengths(audio_lengths), q.lo, q.scale(),

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DMEL_ABI_VERSION 3
+#define DMEL_ABI_VERSION 4
 
 #define DMEL_OK 0
 #define DMEL_ERR_INVALID (-1)     /* bad argument (shape, null pointer, L <= reflect pad ...) */
@@ -105,6 +105,17 @@ int dmel_encode_u8(dmel_plan* plan, const float* wav_dev, long long n_rows, long
                    uint8_t* codes_dev, float* logmel_dev,
                    unsigned long long* near_edge_dev, float edge_eps, void* stream);
 
+/* dmel_encode_u8 for int16 PCM waveforms (the format audio is stored and shipped in): value = sample / 32768,
+ * the scale is folded into the window taps, so the codes are bit-identical to dmel_encode_u8 on the
+ * float32 tensor x / 32768.  Half the bytes per sample over PCIe and from HBM.  Where the reference
+ * converts decoded PCM to float32 on the host (dataset/lhotse_tts_dataset.py:29-33, then
+ * models/codec_lit_modules.py:487 `audios.float()`), this takes the PCM directly.
+ * DMEL_ERR_UNSUPPORTED if the geometry does not fit the register-lean kernel variant. */
+int dmel_encode_pcm16_u8(dmel_plan* plan, const int16_t* wav_dev, long long n_rows, long long n_samples,
+                         long long row_stride, const int32_t* lengths_dev,
+                         const float* lo_dev, const float* scale_dev, int n_bins,
+                         uint8_t* codes_dev, void* stream);
+
 /* Windowed form for streaming: writes frames [t_begin, t_begin + t_count) only (t_count < 0 = to the
  * end), for rows of which only samples [src_base, n_samples) are resident, at wav_dev[row][0 ...].
  * n_samples is the row length the reflect padding refers to: while a stream is open pass the number
@@ -148,6 +159,12 @@ int dmel_encode_host_u8(dmel_plan* plan, const float* wav_host, long long n_rows
                         long long row_stride, const int32_t* lengths_host,
                         const float* lo_host, const float* scale_host, int n_bins,
                         uint8_t* codes_host);
+
+/* dmel_encode_host_u8 for int16 PCM host buffers. */
+int dmel_encode_host_pcm16_u8(dmel_plan* plan, const int16_t* wav_host, long long n_rows, long long n_samples,
+                              long long row_stride, const int32_t* lengths_host,
+                              const float* lo_host, const float* scale_host, int n_bins,
+                              uint8_t* codes_host);
 
 /* Stand-alone quantiser stages on an existing (B, n_mels, T) log-mel tensor. */
 int dmel_quantize_u8(const float* logmel_dev, long long n_rows, int n_mels, long long n_frames,

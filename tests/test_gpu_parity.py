@@ -409,3 +409,30 @@ def test_dynamic_tile_schedule_matches_static(d, monkeypatch):
         got, _ = tok.encode(wav, lengths)
         assert torch.equal(got, want)
     assert torch.equal(tok.mel_transform(wav), want_mel)
+
+
+@pytest.mark.parametrize("name,n_bins", [("cfg2_24k_128", 16), ("cfg1_16k_80", 16), ("cfg5_44k_160", 32)])
+def test_pcm16_input_matches_float_path(d, name, n_bins):
+    """int16 PCM in (device and host entry points) gives the same bytes as the float32 path on
+    sample / 32768, including ragged lengths, odd row lengths and a strided batch."""
+    kw = GOLDEN_GEOMETRY[name]
+    n = kw["sample_rate"] * 2 + 1237
+    g = torch.Generator().manual_seed(17)
+    pcm = (torch.randn(6, n, generator=g) * 6000).clamp(-32768, 32767).to(torch.int16)
+    pcm[1, 5000:9000] = 0                       # digital silence: the clamp floor
+    pcm[2] = torch.randint(-32768, 32768, (n,), generator=g).to(torch.int16)  # full scale
+    lengths = torch.tensor([n, n - 1, n // 2, 3000, n, 1], dtype=torch.int32)
+    tok = _tokenizer(d, kw, n_bins)
+    as_float = pcm.float() / 32768.0
+    tok.calibrate([as_float.cuda()])
+    want, want_len = tok.encode(as_float.cuda(), lengths.cuda())
+    got, got_len = tok.encode_pcm16(pcm.cuda(), lengths.cuda())
+    assert torch.equal(got, want) and torch.equal(got_len, want_len)
+    assert torch.equal(tok.encode_pcm16(pcm.cuda()[:, None, :])[0], tok.encode(as_float.cuda())[0])   # (B, 1, L), no lengths
+    wide = torch.zeros(6, n + 40, dtype=torch.int16, device="cuda")
+    wide[:, :n] = pcm.cuda()
+    assert torch.equal(tok.encode_pcm16(wide[:, :n], lengths.cuda())[0], want)    # row stride > row length
+    host = tok.encode_host(pcm.pin_memory(), lengths)                              # int16 host buffers
+    assert torch.equal(host, want.cpu())
+    with pytest.raises(ValueError):
+        tok.encode_pcm16(as_float.cuda())
