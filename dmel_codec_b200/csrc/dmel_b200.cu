@@ -75,6 +75,7 @@ struct dmel_plan {
   mutable std::atomic<unsigned> sched_turn{0};
   // scratch for the host-buffer entry point (grown on demand)
   cudaStream_t streams[2] = {nullptr, nullptr};
+  cudaEvent_t stats_ready = nullptr;
   float* d_wav[2] = {nullptr, nullptr};
   uint8_t* d_codes[2] = {nullptr, nullptr};
   int32_t* d_len[2] = {nullptr, nullptr};
@@ -445,6 +446,7 @@ void dmel_plan_destroy(dmel_plan* plan) {
     cudaFree(plan->d_len[i]);
     if (plan->streams[i]) cudaStreamDestroy(plan->streams[i]);
   }
+  if (plan->stats_ready) cudaEventDestroy(plan->stats_ready);
   cudaFree(plan->d_lo);
   cudaFree(plan->d_scale);
   delete plan;
@@ -753,12 +755,12 @@ static int encode_host_impl(dmel_plan* plan, const void* wav_host_v, int elem, l
     DMEL_CUDA(cudaMalloc((void**)&plan->d_lo, plan->n_mels * sizeof(float)));
     DMEL_CUDA(cudaMalloc((void**)&plan->d_scale, plan->n_mels * sizeof(float)));
   }
-  // rows per chunk: a few MiB of waveform (DMEL_HOST_CHUNK_MB, default 16), so copies and kernels of
-  // neighbouring chunks overlap and the un-overlapped tail (last kernel + last D2H) stays short
+  // rows per chunk: at least four chunks per call so copies and kernels of neighbouring chunks overlap and the
+  // un-overlapped tail (last kernel + last D2H) stays short, at most 16 MiB of waveform each (DMEL_HOST_CHUNK_MB pins it)
   const long long row_bytes = n_samples * elem;
-  long long chunk_mb = 16;
-  if (const char* env = std::getenv("DMEL_HOST_CHUNK_MB")) chunk_mb = std::max(1, std::atoi(env));
-  long long chunk_rows = std::max<long long>(1, (chunk_mb << 20) / row_bytes);
+  long long chunk_bytes = std::min<long long>(16ll << 20, std::max<long long>(2ll << 20, row_bytes * n_rows / 4));
+  if (const char* env = std::getenv("DMEL_HOST_CHUNK_MB")) chunk_bytes = (long long)std::max(1, std::atoi(env)) << 20;
+  long long chunk_rows = std::max<long long>(1, chunk_bytes / row_bytes);
   chunk_rows = std::min(chunk_rows, n_rows);
   const size_t wav_need = (size_t)chunk_rows * n_samples;
   const size_t codes_need = (size_t)chunk_rows * plan->n_mels * T;
@@ -786,9 +788,13 @@ static int encode_host_impl(dmel_plan* plan, const void* wav_host_v, int elem, l
     }
     plan->len_cap = chunk_rows;
   }
+  // both streams were synchronised when the previous call returned, so nothing still reads d_lo / d_scale; the
+  // second stream waits for the statistics through an event instead of a host synchronisation
   DMEL_CUDA(cudaMemcpyAsync(plan->d_lo, lo_host, plan->n_mels * sizeof(float), cudaMemcpyHostToDevice, plan->streams[0]));
   DMEL_CUDA(cudaMemcpyAsync(plan->d_scale, scale_host, plan->n_mels * sizeof(float), cudaMemcpyHostToDevice, plan->streams[0]));
-  DMEL_CUDA(cudaStreamSynchronize(plan->streams[0]));
+  if (!plan->stats_ready) DMEL_CUDA(cudaEventCreateWithFlags(&plan->stats_ready, cudaEventDisableTiming));
+  DMEL_CUDA(cudaEventRecord(plan->stats_ready, plan->streams[0]));
+  DMEL_CUDA(cudaStreamWaitEvent(plan->streams[1], plan->stats_ready, 0));
   int slot = 0;
   for (long long r0 = 0; r0 < n_rows; r0 += chunk_rows, slot ^= 1) {
     const long long rows = std::min(chunk_rows, n_rows - r0);

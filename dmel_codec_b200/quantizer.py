@@ -107,6 +107,14 @@ class DMelQuantizer(nn.Module):
             self._derived["scale"] = torch.where(width > 0, k / width, torch.zeros_like(width))
         return self._derived["scale"]
 
+    def host_stats(self):
+        """(lo, scale) as CPU float32 tensors, copied from the device once per calibration (the
+        host-buffer encode hands them to the library by host pointer)."""
+        if "host_stats" not in self._derived:
+            self._derived["host_stats"] = (self.lo.detach().to("cpu", torch.float32).contiguous(),
+                                           self.scale().detach().to("cpu", torch.float32).contiguous())
+        return self._derived["host_stats"]
+
     def table(self) -> Tensor:
         """(n_mels, K) bin centres, separate multiply and add (no FMA)."""
         if "table" not in self._derived:
@@ -218,7 +226,8 @@ class DMelTokenizer(nn.Module):
         float32 waveforms, or int16 PCM (value = sample / 32768: half the PCIe bytes, same codes)."""
         q = self.quantizer
         q._check_ready()
-        return self._plan(q.lo.device).encode_host(audios, self._flat_lengths(audio_lengths), q.lo, q.scale(),
+        lo_h, scale_h = q.host_stats()
+        return self._plan(q.lo.device).encode_host(audios, self._flat_lengths(audio_lengths), lo_h, scale_h,
                                                    q.n_bins, out)
 
     @torch.no_grad()
