@@ -147,6 +147,40 @@ def run_reference(args, rank: int):
     }))
 
 
+def pin_to_gpu_numa_node(local_rank: int):
+    """Run this rank on the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI device) so the pinned
+    host buffers of the e2e leg are allocated on, and copied from, the memory of that NUMA node."""
+    if os.environ.get("DMEL_BENCH_NO_AFFINITY"):
+        return None
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id  # torch >= 2.x
+    except Exception:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        except Exception:
+            return None
+    try:
+        bus = str(bus).lower()
+        if len(bus.split(":")[0]) == 8:  # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return spec
+    except (OSError, ValueError):
+        pass
+    return None
+
+
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch.distributed as dist
     import dmel_codec_b200 as d
@@ -156,6 +190,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         raise SystemExit("bench.py needs a CUDA device: dmel_codec_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = pin_to_gpu_numa_node(local_rank) if world > 1 else None
     tok = d.DMelTokenizer(n_bins=N_BINS, **GEOM).to(dev)
 
     # this rank's shard: utterance ids [rank*RING*BATCH, ...): RING distinct batches
@@ -273,7 +308,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": f"{BATCH}x{SECONDS}s", "sharding": "utterances, no data-path collective",
                    "l2": f"inputs cycle through a ring of {RING} distinct batches ({RING * ENCODE_BYTES / 1e6:.0f} MB > 126 MB L2)",
-                   "wall_ms_per_step": wall_ms / args.steps},
+                   "wall_ms_per_step": wall_ms / args.steps, "rank0_cpu_affinity": affinity},
         "roofline": {"bound": "hbm", "kernel": f"dmel_fused_kernel<{GEOM['n_fft']},{launch_cfg['tile_frames']},codes> "
                      f"({launch_cfg['ctas_per_sm']} CTA/SM, {launch_cfg['smem_bytes']} B smem)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
