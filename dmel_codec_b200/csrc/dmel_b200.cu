@@ -483,7 +483,8 @@ int dmel_logmel_f32(dmel_plan* plan, const float* wav_dev, long long n_rows, lon
 }
 
 int dmel_logmel_masked(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
-                       long long row_stride, const int32_t* lengths_dev, int out_dtype, void* out_dev, void* stream) {
+                       long long row_stride, const int32_t* lengths_dev, int out_dtype, void* out_dev,
+                       float* row_sum_dev, void* stream) {
   FusedParams p;
   int grid = 0;
   int rc = prepare_fused(plan, wav_dev, n_rows, n_samples, row_stride, &p, &grid);
@@ -495,6 +496,7 @@ int dmel_logmel_masked(dmel_plan* plan, const float* wav_dev, long long n_rows, 
   p.logmel = static_cast<float*>(out_dev);
   p.lengths = lengths_dev;
   p.mask_invalid = lengths_dev != nullptr;
+  p.row_sum = row_sum_dev;
   DeviceGuard guard(plan->device);
   DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream, out_dtype == DMEL_DTYPE_BF16));
   return DMEL_OK;

@@ -63,6 +63,7 @@ struct FusedParams {
   const int* lengths;       // valid samples per row, or null
   float* logmel;            // (B, M, T)            [kOutLogmel]; __nv_bfloat16 with kOutBf16
   int mask_invalid;         // log-mel of frames at or past lengths[b] / hop is written as 0 (the caller's mel * mask)
+  float* row_sum;           // (B, M) or null: += sum over the frames of each row and channel of the log-mel as written [kOutLogmel]
   unsigned char* codes;     // (B, M, T)            [kOutCodes]
   const float* q_lo;        // (M)                  [kOutCodes]
   const float* q_scale;     // (M)  K / (hi - lo)   [kOutCodes]
@@ -582,7 +583,14 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
           } while (x4 != x4_end);
           const float value = fast_log(fmaxf(acc, kLogClip));
           if constexpr (kLogmel) {
-            if (live && in_row) store_logmel(o, (p.mask_invalid && !valid) ? 0.f : value);
+            const float out = (p.mask_invalid && !valid) ? 0.f : value;
+            if (live && in_row) store_logmel(o, out);
+            if (p.row_sum) {  // per (row, channel) sum over time: the caller's mels.mean(-1) without another pass
+              float part = (live && in_row) ? out : 0.f;
+#pragma unroll
+              for (int d = TF / 2; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+              if (fr == 0 && live) atomicAdd(p.row_sum + (size_t)cur.row * p.n_mels + m, part);
+            }
           }
           if constexpr (kCodes) {
             const float sc = *scp;

@@ -111,7 +111,7 @@ class Plan:
         return out
 
     def logmel_masked(self, wav: torch.Tensor, lengths: Optional[torch.Tensor],
-                      dtype: torch.dtype = torch.float32) -> torch.Tensor:
+                      dtype: torch.dtype = torch.float32, row_sum: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Log-mel in ``dtype`` (float32 or bfloat16) with frames at or past ``lengths // hop``
         zeroed, in one launch (``dmel_logmel_masked``)."""
         _require_cuda(wav, "audio")
@@ -124,7 +124,8 @@ class Plan:
         len_ptr = self._lengths_ptr(lengths, b, rows.device)
         _native.check(_native.load().dmel_logmel_masked(
             self._handle, rows.data_ptr(), b, n, rows.stride(0) if b > 1 else n, len_ptr[0],
-            1 if dtype == torch.bfloat16 else 0, out.data_ptr(), _stream_ptr(rows.device)))
+            1 if dtype == torch.bfloat16 else 0, out.data_ptr(),
+            row_sum.data_ptr() if row_sum is not None else None, _stream_ptr(rows.device)))
         return out
 
     # -- calibration pass ---------------------------------------------------

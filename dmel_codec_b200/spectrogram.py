@@ -96,3 +96,20 @@ class LogMelSpectrogram(nn.Module):
                                f"got device {audios.device}")
         mels = self.spectrogram.plan_for(audios.device).logmel_masked(audios, audio_lengths, dtype)
         return mels, audio_lengths // self.hop_length
+
+    @torch.no_grad()
+    def with_quality(self, audios: Tensor):
+        """``(mels, quality)`` of ``VQGAN.training_step`` (reference models/codec_lit_modules.py:171-174):
+        ``quality = ((mels.mean(-1) > -8).sum(-1) - 90) / 10`` with the per-channel time sums
+        accumulated by the same launch that writes the mel (one transform call serves both the
+        reference's identically configured ``encode_mel_transform`` and ``gt_mel_transform``)."""
+        if not audios.is_cuda:
+            raise RuntimeError("dmel_codec_b200.LogMelSpectrogram needs a CUDA tensor (no CPU fallback); "
+                               f"got device {audios.device}")
+        plan = self.spectrogram.plan_for(audios.device)
+        b = audios.shape[0]
+        sums = torch.zeros((b, self.n_mels), dtype=torch.float32, device=audios.device)
+        mels = plan.logmel_masked(audios, None, torch.float32, row_sum=sums)
+        quality = ((sums / mels.shape[-1] > -8).sum(-1) - 90) / 10
+        return mels, quality.unsqueeze(-1)
+

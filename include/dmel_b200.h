@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DMEL_ABI_VERSION 4
+#define DMEL_ABI_VERSION 5
 
 #define DMEL_OK 0
 #define DMEL_ERR_INVALID (-1)     /* bad argument (shape, null pointer, L <= reflect pad ...) */
@@ -77,10 +77,14 @@ int dmel_logmel_f32(dmel_plan* plan, const float* wav_dev, long long n_rows, lon
  * (DMEL_DTYPE_F32) or bfloat16 (DMEL_DTYPE_BF16, round-to-nearest-even of the float32 value).
  * lengths_dev NULL = no masking.  Replaces the transform + cast + sequence_mask multiply of
  * VQGAN.encode_unquantized (reference models/codec_lit_modules.py:486-507, mask rule
- * utils/utils.py:48-55); the caller's (B*G, n_mels/G, T) group view of the result is free. */
+ * utils/utils.py:48-55); the caller's (B*G, n_mels/G, T) group view of the result is free.
+ * row_sum_dev (optional, (B, n_mels) float32, zeroed by the caller): += the sum over time of the
+ * values written, per row and channel - the mels.mean(-1) behind the training step's `quality`
+ * statistic (models/codec_lit_modules.py:173) without another pass over the mel (float atomics:
+ * the summation order, hence the last bit, varies from launch to launch). */
 int dmel_logmel_masked(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
                        long long row_stride, const int32_t* lengths_dev, int out_dtype,
-                       void* out_dev, void* stream);
+                       void* out_dev, float* row_sum_dev, void* stream);
 
 /* Calibration pass: running per-channel min / max of the log-mel of this batch
  * over valid frames (t < lengths[b] / hop; lengths_dev may be NULL = all T).

@@ -436,3 +436,21 @@ def test_pcm16_input_matches_float_path(d, name, n_bins):
     assert torch.equal(host, want.cpu())
     with pytest.raises(ValueError):
         tok.encode_pcm16(as_float.cuda())
+
+
+def test_quality_statistic_from_fused_sums(d):
+    """LogMelSpectrogram.with_quality == the reference training step's quality on the same mel
+    (models/codec_lit_modules.py:171-174), from sums the mel launch accumulates itself."""
+    from dmel_codec_b200 import synth
+    kw = GOLDEN_GEOMETRY["cfg2_24k_128"]
+    wav = synth.batch(range(730, 738), 24000 * 3 + 11, 24000, "speech").cuda()
+    wav[5] *= 1e-3   # a quiet utterance: fewer channels above the -8 threshold
+    mt = d.LogMelSpectrogram(**kw).cuda()
+    mels, quality = mt.with_quality(wav)
+    assert torch.equal(mels, mt(wav))
+    mean = mels.mean(-1)
+    want = ((mean > -8).sum(-1) - 90) / 10
+    near = ((mean + 8).abs() < 1e-4).any(-1)          # a channel mean sitting on the threshold may flip
+    assert quality.shape == (8, 1)
+    assert torch.equal(quality[~near, 0], want[~near].to(quality.dtype))
+    assert len(set(quality[:, 0].tolist())) > 1          # the statistic discriminates in this batch
