@@ -42,6 +42,8 @@ struct FastDiv {
 __global__ void __launch_bounds__(kStreamThreads) dequantize_kernel(
     const uint8_t* __restrict__ codes, float* __restrict__ out, const float* __restrict__ table,
     unsigned n_elems, FastDiv by_frames, FastDiv by_mels, unsigned n_bins, bool vec_ok) {
+  grid_dependency_wait();   // programmatic dependent launch: the inputs may come from the previous kernel
+  grid_launch_dependents();
   const unsigned n_frames = by_frames.d, n_mels = by_mels.d;
   const unsigned groups = n_elems >> 2;
   const unsigned stride = gridDim.x * kStreamThreads;
@@ -96,6 +98,8 @@ __global__ void __launch_bounds__(kStreamThreads) quantize_kernel(
     const float* __restrict__ mel, uint8_t* __restrict__ codes, const float* __restrict__ lo,
     const float* __restrict__ scale, unsigned n_elems, FastDiv by_frames, FastDiv by_mels,
     unsigned n_bins, bool vec_ok) {
+  grid_dependency_wait();   // programmatic dependent launch: the inputs may come from the previous kernel
+  grid_launch_dependents();
   const unsigned n_frames = by_frames.d, n_mels = by_mels.d;
   const unsigned groups = n_elems >> 2;
   const unsigned stride = gridDim.x * kStreamThreads;
@@ -142,6 +146,8 @@ __global__ void __launch_bounds__(kStreamThreads) quantize_kernel(
 __global__ void __launch_bounds__(kStreamThreads) tensor_minmax_kernel(
     const float* __restrict__ mel, const int* __restrict__ n_valid, float* run_min, float* run_max,
     unsigned n_lines, unsigned n_frames, unsigned n_mels) {
+  grid_dependency_wait();   // programmatic dependent launch: the inputs may come from the previous kernel
+  grid_launch_dependents();
   const unsigned warps_per_block = kStreamThreads / 32;
   const unsigned lane = threadIdx.x & 31;
   for (unsigned line = blockIdx.x * warps_per_block + (threadIdx.x >> 5); line < n_lines;

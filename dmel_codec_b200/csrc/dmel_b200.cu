@@ -10,6 +10,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -39,6 +40,26 @@ int fail(int code, const char* fmt, ...) {
       return fail(DMEL_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
                   __FILE__, __LINE__);                                                   \
   } while (0)
+
+// Every kernel of this library is launched with the programmatic-stream-serialisation attribute: when the
+// previous operation of the stream is one of our kernels (they all execute griddepcontrol.launch_dependents),
+// the launch latency and the plan-constant prologue of this one overlap its tail; each kernel executes
+// griddepcontrol.wait before it touches caller memory.  DMEL_NO_PDL=1 gives ordinary launches.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool pdl = std::getenv("DMEL_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 template <typename T>
 cudaError_t upload(T** dev, const std::vector<T>& host) {
@@ -157,8 +178,7 @@ struct Launch {
       if (e != cudaSuccess) return e;
       plan->smem_opt_in |= 1ull << MODE;
     }
-    kern<<<grid, dmel::kThreads, plan->smem_bytes, st>>>(*p);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3(grid), dim3(dmel::kThreads), plan->smem_bytes, st, *p);
   }
 };
 
@@ -859,9 +879,9 @@ int dmel_quantize_u8(const float* logmel_dev, long long n_rows, int n_mels, long
   if (!lo_dev || !scale_dev) return fail(DMEL_ERR_INVALID, "lo_dev / scale_dev is null");
   if (n == 0) return DMEL_OK;
   const bool vec = ((reinterpret_cast<uintptr_t>(logmel_dev) & 15) == 0) && ((reinterpret_cast<uintptr_t>(codes_dev) & 3) == 0);
-  dmel::quantize_kernel<<<stream_grid(nullptr, n >> 2), dmel::kStreamThreads, 0, (cudaStream_t)stream>>>(
-      logmel_dev, codes_dev, lo_dev, scale_dev, n, dmel::FastDiv::make((unsigned)n_frames), dmel::FastDiv::make((unsigned)n_mels), (unsigned)n_bins, vec);
-  DMEL_CUDA(cudaGetLastError());
+  DMEL_CUDA(launch_pdl(dmel::quantize_kernel, dim3(stream_grid(nullptr, n >> 2)), dim3(dmel::kStreamThreads), 0, (cudaStream_t)stream,
+                       logmel_dev, codes_dev, lo_dev, scale_dev, n, dmel::FastDiv::make((unsigned)n_frames),
+                       dmel::FastDiv::make((unsigned)n_mels), (unsigned)n_bins, vec));
   return DMEL_OK;
 }
 
@@ -874,9 +894,9 @@ int dmel_dequantize_f32(const uint8_t* codes_dev, long long n_rows, int n_mels, 
   if (!table_dev) return fail(DMEL_ERR_INVALID, "table_dev is null");
   if (n == 0) return DMEL_OK;
   const bool vec = ((reinterpret_cast<uintptr_t>(logmel_dev) & 15) == 0) && ((reinterpret_cast<uintptr_t>(codes_dev) & 3) == 0);
-  dmel::dequantize_kernel<<<stream_grid(nullptr, n >> 2), dmel::kStreamThreads, 0, (cudaStream_t)stream>>>(
-      codes_dev, logmel_dev, table_dev, n, dmel::FastDiv::make((unsigned)n_frames), dmel::FastDiv::make((unsigned)n_mels), (unsigned)n_bins, vec);
-  DMEL_CUDA(cudaGetLastError());
+  DMEL_CUDA(launch_pdl(dmel::dequantize_kernel, dim3(stream_grid(nullptr, n >> 2)), dim3(dmel::kStreamThreads), 0, (cudaStream_t)stream,
+                       codes_dev, logmel_dev, table_dev, n, dmel::FastDiv::make((unsigned)n_frames),
+                       dmel::FastDiv::make((unsigned)n_mels), (unsigned)n_bins, vec));
   return DMEL_OK;
 }
 
@@ -889,9 +909,8 @@ int dmel_tensor_minmax_f32(const float* logmel_dev, long long n_rows, int n_mels
   if (n == 0) return DMEL_OK;
   const unsigned lines = (unsigned)(n_rows * n_mels);
   const int blocks = (int)std::min<unsigned>((lines + 7) / 8, 148u * 8u);
-  dmel::tensor_minmax_kernel<<<blocks, dmel::kStreamThreads, 0, (cudaStream_t)stream>>>(
-      logmel_dev, n_valid_dev, min_dev, max_dev, lines, (unsigned)n_frames, (unsigned)n_mels);
-  DMEL_CUDA(cudaGetLastError());
+  DMEL_CUDA(launch_pdl(dmel::tensor_minmax_kernel, dim3(blocks), dim3(dmel::kStreamThreads), 0, (cudaStream_t)stream,
+                       logmel_dev, n_valid_dev, min_dev, max_dev, lines, (unsigned)n_frames, (unsigned)n_mels));
   return DMEL_OK;
 }
 

@@ -103,6 +103,13 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
+// ---- programmatic dependent launch -------------------------------------------------
+// launch_dependents: the next kernel of the stream (if it was launched with the programmatic-serialisation
+// attribute) may start once every CTA of this grid has passed this point; grid_dependency_wait: block until the
+// previous kernel of the stream has completed and its writes are visible.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- mbarrier + bulk async copy (TMA engine, 1-D) ----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -232,6 +239,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   const int lane = tid & 31;
   const int warp = tid >> 5;
   float2* my_tile = tiles + warp * LY::kTileF2;
+  grid_launch_dependents();
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -326,22 +334,12 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
     }
   };
 
-  // The first tile's samples leave HBM before anything else; the per-CTA constants (L2 resident after
-  // the first CTAs) are fetched while that copy is in flight.
-  int tile = blockIdx.x;
-  TileInfo cur = describe(tile < p.n_tiles ? tile : 0);
-#ifndef DMEL_LATE_FIRST_STAGE
-  if (tile < p.n_tiles) stage(cur, 0);
-#endif
-
   // ---- per-CTA constants -------------------------------------------------
+  // Everything up to grid_dependency_wait() reads plan-owned memory only (written at plan creation), so under
+  // programmatic dependent launch it overlaps the tail of the previous kernel in the stream.
   for (int i = tid; i < p.n_chan_pad; i += kThreads) {
     s_chan[i] = p.chan[i];
-    if constexpr (kCodes) {
-      const bool real = i < p.n_mels;
-      s_lo[i] = real ? p.q_lo[i] : 0.f;
-      s_scale[i] = real ? p.q_scale[i] : 0.f;
-    } else {
+    if constexpr (!kCodes) {
       s_min[i] = __int_as_float(0x7f800000);
       s_max[i] = __int_as_float(0xff800000);
     }
@@ -354,10 +352,18 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   if constexpr (NFFT == 2048 && !kSplit) {
     for (int i = tid; i < LY::kFoldN; i += kThreads) s_fold[i] = p.fold_tw[i];
   }
-  __syncthreads();  // constants + barrier init visible
-#ifdef DMEL_LATE_FIRST_STAGE
+  grid_dependency_wait();  // from here on: the caller's tensors (waveform, lengths, statistics, outputs, tile counter)
+  if constexpr (kCodes) {
+    for (int i = tid; i < p.n_chan_pad; i += kThreads) {
+      const bool real = i < p.n_mels;
+      s_lo[i] = real ? p.q_lo[i] : 0.f;
+      s_scale[i] = real ? p.q_scale[i] : 0.f;
+    }
+  }
+  int tile = blockIdx.x;
+  TileInfo cur = describe(tile < p.n_tiles ? tile : 0);
   if (tile < p.n_tiles) stage(cur, 0);
-#endif
+  __syncthreads();  // constants + barrier init visible
   // Tiles after the first are handed out by a global counter (lean variants), so the CTAs of the
   // grid finish within one tile of each other instead of one or two tiles apart.
   constexpr bool kDynamic = LY::kWaveBufs == 1;
