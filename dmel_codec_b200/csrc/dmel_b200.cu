@@ -197,9 +197,11 @@ cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int gr
   if (p.near_edge) mode |= kOutEdge;
   if (bf16_logmel) mode |= kOutBf16;
   if (pcm16) mode |= kInPcm16;
+  if (p.dequant) mode |= kOutDequant;
   switch (mode) {
     case kOutCodes: return launch_fused_mode<kOutCodes>(plan, p, grid, st);
     case kOutCodes | kInPcm16: return launch_fused_mode<kOutCodes | kInPcm16>(plan, p, grid, st);
+    case kOutCodes | kOutDequant: return launch_fused_mode<kOutCodes | kOutDequant>(plan, p, grid, st);
     case kOutLogmel: return launch_fused_mode<kOutLogmel>(plan, p, grid, st);
     case kOutLogmel | kOutBf16: return launch_fused_mode<kOutLogmel | kOutBf16>(plan, p, grid, st);
     case kOutStats: return launch_fused_mode<kOutStats>(plan, p, grid, st);
@@ -559,6 +561,31 @@ int dmel_encode_u8(dmel_plan* plan, const float* wav_dev, long long n_rows, long
   p.logmel = logmel_dev;
   p.near_edge = near_edge_dev;
   p.edge_eps = edge_eps;
+  DeviceGuard guard(plan->device);
+  DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream));
+  return DMEL_OK;
+}
+
+int dmel_encode_decode_u8(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
+                          long long row_stride, const int32_t* lengths_dev, const float* lo_dev,
+                          const float* scale_dev, const float* step_dev, int n_bins, uint8_t* codes_dev,
+                          float* mel_hat_dev, void* stream) {
+  FusedParams p;
+  int grid = 0;
+  int rc = prepare_fused(plan, wav_dev, n_rows, n_samples, row_stride, &p, &grid);
+  if (rc != DMEL_OK) return rc;
+  if ((rc = check_bins(n_bins)) != DMEL_OK) return rc;
+  if (!lo_dev || !scale_dev || !step_dev || !codes_dev || !mel_hat_dev)
+    return fail(DMEL_ERR_INVALID, "lo_dev / scale_dev / step_dev / codes_dev / mel_hat_dev is null");
+  if (n_rows == 0) return DMEL_OK;
+  p.lengths = lengths_dev;
+  p.q_lo = lo_dev;
+  p.q_scale = scale_dev;
+  p.q_step = step_dev;
+  p.n_bins = n_bins;
+  p.kmax = float(n_bins - 1);
+  p.codes = codes_dev;
+  p.dequant = mel_hat_dev;
   DeviceGuard guard(plan->device);
   DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream));
   return DMEL_OK;

@@ -36,6 +36,7 @@ constexpr int kOutLogmel = 2;
 constexpr int kOutStats = 4;
 constexpr int kOutEdge = 8;  // count values within edge_eps of an interior bin edge (needs kOutCodes)
 constexpr int kOutBf16 = 16;  // the log-mel output tensor is bfloat16 (needs kOutLogmel)
+constexpr int kOutDequant = 64;  // also write the bin centre of every code, float32 (needs kOutCodes): the quantiser's forward
 constexpr int kInPcm16 = 32;  // the waveform is int16 PCM (x / 32768 is folded into the window taps); lean variants only
 
 struct FusedParams {
@@ -67,6 +68,8 @@ struct FusedParams {
   unsigned char* codes;     // (B, M, T)            [kOutCodes]
   const float* q_lo;        // (M)                  [kOutCodes]
   const float* q_scale;     // (M)  K / (hi - lo)   [kOutCodes]
+  const float* q_step;      // (M)  (hi - lo) / K   [kOutDequant]
+  float* dequant;           // (B, M, T) lo + (code + 0.5) * step, 0 past the valid frames [kOutDequant]
   int n_bins;
   float kmax;               // float(n_bins - 1)
   // byte offsets of the shared-memory regions (FusedLayout, filled in by the host so the kernel
@@ -176,7 +179,7 @@ struct FusedLayout {
     return align16(weights_off(wave_len, n_chan) + size_t(nnz) * 4);
   }
   static __host__ __device__ size_t bar_off(int wave_len, int n_chan, int nnz) {
-    return align16(perchan_off(wave_len, n_chan, nnz) + size_t(n_chan) * 8);  // {lo, scale} or {min, max}
+    return align16(perchan_off(wave_len, n_chan, nnz) + size_t(n_chan) * 12);  // {lo, scale, step} or {min, max}
   }
   static __host__ __device__ size_t total(int wave_len, int n_chan, int nnz) {
     return bar_off(wave_len, n_chan, nnz) + 32;  // two mbarriers + the next-tile slot
@@ -208,6 +211,8 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   constexpr bool kStats = (MODE & kOutStats) != 0, kEdge = (MODE & kOutEdge) != 0;
   constexpr bool kBf16 = (MODE & kOutBf16) != 0;
   constexpr bool kPcm = (MODE & kInPcm16) != 0;
+  constexpr bool kDequant = (MODE & kOutDequant) != 0;
+  static_assert(!kDequant || kCodes, "kOutDequant qualifies the code output");
   static_assert(!kPcm || kLean, "int16 input is built for the register-lean variants");
   using wave_t = std::conditional_t<kPcm, short, float>;
   constexpr int kAlign = 16 / (int)sizeof(wave_t);  // samples per 16 bytes: granularity of the bulk copies
@@ -231,6 +236,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   static_assert(!(kCodes && kStats), "codes and statistics share their per-channel scratch");
   float* s_lo = reinterpret_cast<float*>(smem + p.off_perchan);
   float* s_scale = s_lo + p.n_chan_pad;
+  float* s_step = s_scale + p.n_chan_pad;
   float* s_min = s_lo;
   float* s_max = s_scale;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
@@ -358,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
       const bool real = i < p.n_mels;
       s_lo[i] = real ? p.q_lo[i] : 0.f;
       s_scale[i] = real ? p.q_scale[i] : 0.f;
+      if constexpr (kDequant) s_step[i] = real ? p.q_step[i] : 0.f;
     }
   }
   int tile = blockIdx.x;
@@ -562,6 +569,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
           for (int m = m0; m < p.n_mels; m += kStep, o += ostep)
             if (in_row) {
               if constexpr (kCodes) p.codes[o] = 0;
+              if constexpr (kDequant) p.dequant[o] = 0.f;
               if constexpr (kLogmel) store_logmel(o, 0.f);
             }
         }
@@ -603,6 +611,10 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
             const float pos = __fmul_rn(__fsub_rn(value, *lop), sc);
             const float q = fminf(fmaxf(floorf(pos), 0.f), p.kmax);
             if (live && in_row) p.codes[o] = valid ? (unsigned char)q : (unsigned char)0;
+            if constexpr (kDequant) {  // the table entry the stand-alone decoder would look up, same two roundings
+              const float centre = __fadd_rn(*lop, __fmul_rn(q + 0.5f, s_step[m]));
+              if (live && in_row) p.dequant[o] = valid ? centre : 0.f;
+            }
             if constexpr (kEdge) {
               const float e = fminf(fmaxf(rintf(pos), 1.f), p.kmax);
               if (live && valid && fabsf(pos - e) < p.edge_eps * sc) ++edge_hits;

@@ -159,6 +159,22 @@ class Plan:
             _stream_ptr(rows.device)))
         return (codes, logmel) if return_logmel else codes
 
+    def encode_decode(self, wav: torch.Tensor, lengths: Optional[torch.Tensor], lo: torch.Tensor, scale: torch.Tensor,
+                      step: torch.Tensor, n_bins: int):
+        """(codes, mel_hat): codes as ``encode`` and the bin centre of every code, one launch."""
+        _require_cuda(wav, "audio")
+        rows = as_rows(wav)
+        b, n = rows.shape
+        t = self._frames_or_raise(n)
+        codes = torch.empty((b, self.n_mels, t), dtype=torch.uint8, device=rows.device)
+        mel_hat = torch.empty((b, self.n_mels, t), dtype=torch.float32, device=rows.device)
+        len_ptr = self._lengths_ptr(lengths, b, rows.device)
+        _native.check(_native.load().dmel_encode_decode_u8(
+            self._handle, rows.data_ptr(), b, n, rows.stride(0) if b > 1 else n, len_ptr[0],
+            lo.data_ptr(), scale.data_ptr(), step.data_ptr(), int(n_bins), codes.data_ptr(), mel_hat.data_ptr(),
+            _stream_ptr(rows.device)))
+        return codes, mel_hat
+
     def encode_pcm16(self, wav: torch.Tensor, lengths: Optional[torch.Tensor], lo: torch.Tensor,
                      scale: torch.Tensor, n_bins: int) -> torch.Tensor:
         """int16 PCM (value = sample / 32768) -> codes; bit-identical to ``encode(wav.float() / 32768)``."""

@@ -107,6 +107,12 @@ class DMelQuantizer(nn.Module):
             self._derived["scale"] = torch.where(width > 0, k / width, torch.zeros_like(width))
         return self._derived["scale"]
 
+    def step(self) -> Tensor:
+        """(hi - lo) / K per channel: the bin width the centre table is built from."""
+        if "step" not in self._derived:
+            self._derived["step"] = ((self.hi - self.lo) / float(self.n_bins)).contiguous()
+        return self._derived["step"]
+
     def host_stats(self):
         """(lo, scale) as CPU float32 tensors, copied from the device once per calibration (the
         host-buffer encode hands them to the library by host pointer)."""
@@ -207,6 +213,17 @@ class DMelTokenizer(nn.Module):
         if return_mel:
             return out[0], code_lengths, out[1]
         return out, code_lengths
+
+    @torch.no_grad()
+    def encode_decode(self, audios: Tensor, audio_lengths: Optional[Tensor] = None) -> DMelResult:
+        """The quantiser's forward fused with the transform, one launch: ``codes`` and ``z``, the bin
+        centre of every code (== ``decode(codes, code_lengths)``, bit for bit).  ``latents`` (the
+        pre-quantisation log-mel) never reaches HBM here and is None; ask ``encode(return_mel=True)`` for it."""
+        q = self.quantizer
+        q._check_ready()
+        lengths = self._flat_lengths(audio_lengths)
+        codes, mel_hat = self._plan(audios.device).encode_decode(audios, lengths, q.lo, q.scale(), q.step(), q.n_bins)
+        return DMelResult(z=mel_hat, codes=codes, latents=None)
 
     @torch.no_grad()
     def encode_pcm16(self, audios: Tensor, audio_lengths: Optional[Tensor] = None):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DMEL_ABI_VERSION 5
+#define DMEL_ABI_VERSION 6
 
 #define DMEL_OK 0
 #define DMEL_ERR_INVALID (-1)     /* bad argument (shape, null pointer, L <= reflect pad ...) */
@@ -108,6 +108,16 @@ int dmel_encode_u8(dmel_plan* plan, const float* wav_dev, long long n_rows, long
                    const float* lo_dev, const float* scale_dev, int n_bins,
                    uint8_t* codes_dev, float* logmel_dev,
                    unsigned long long* near_edge_dev, float edge_eps, void* stream);
+
+/* The quantiser's forward in one launch: codes as dmel_encode_u8, and for every code its bin centre
+ * mel_hat = lo_c + (code + 0.5) * step_c (step_c = (hi_c - lo_c) / K supplied by the caller, float32;
+ * multiply and add rounded separately, i.e. bit-identical to dmel_dequantize_f32 on those codes), 0 at frames
+ * at or past lengths[b] / hop.  Mirrors forward() of the reference's quantiser module, which returns the
+ * quantised features together with the indices (models/modules/dowmsample_fsq.py:86-122). */
+int dmel_encode_decode_u8(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
+                          long long row_stride, const int32_t* lengths_dev,
+                          const float* lo_dev, const float* scale_dev, const float* step_dev, int n_bins,
+                          uint8_t* codes_dev, float* mel_hat_dev, void* stream);
 
 /* dmel_encode_u8 for int16 PCM waveforms (the format audio is stored and shipped in): value = sample / 32768,
  * the scale is folded into the window taps, so the codes are bit-identical to dmel_encode_u8 on the

@@ -454,3 +454,23 @@ def test_quality_statistic_from_fused_sums(d):
     assert quality.shape == (8, 1)
     assert torch.equal(quality[~near, 0], want[~near].to(quality.dtype))
     assert len(set(quality[:, 0].tolist())) > 1          # the statistic discriminates in this batch
+
+
+@pytest.mark.parametrize("name,n_bins", [("cfg2_24k_128", 16), ("cfg5_44k_160", 32)])
+def test_fused_forward_equals_encode_then_decode(d, name, n_bins):
+    """DMelTokenizer.encode_decode (one launch) == encode followed by the table-lookup decode, bit for bit,
+    with and without lengths."""
+    from dmel_codec_b200 import synth
+    kw = GOLDEN_GEOMETRY[name]
+    n = kw["sample_rate"] * 2 + 333
+    wav = synth.batch(range(740, 745), n, kw["sample_rate"], "speech").cuda()
+    lengths = torch.tensor([n, n // 2, 5000, n - 1, 0], device="cuda")
+    tok = _tokenizer(d, kw, n_bins)
+    tok.calibrate([wav])
+    codes, code_lengths = tok.encode(wav, lengths)
+    out = tok.encode_decode(wav, lengths)
+    assert torch.equal(out.codes, codes)
+    assert torch.equal(out.z, tok.decode(codes, code_lengths))
+    codes2, _ = tok.encode(wav)
+    out2 = tok.encode_decode(wav)
+    assert torch.equal(out2.codes, codes2) and torch.equal(out2.z, tok.decode(codes2))
