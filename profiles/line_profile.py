@@ -23,8 +23,13 @@ def main():
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
-    h = rows[heads[0]]
-    body = [r for r in rows[heads[0] + 1: heads[1] - 1 if len(heads) > 1 else None] if len(r) == len(h)]
+    pick = 0  # the SASS table of the first dmel_fused_kernel launch if there is one
+    for n, hi in enumerate(heads):
+        if hi > 0 and any("dmel_fused_kernel" in c for c in rows[hi - 1]):
+            pick = n
+            break
+    h = rows[heads[pick]]
+    body = [r for r in rows[heads[pick] + 1: heads[pick + 1] - 1 if len(heads) > pick + 1 else None] if len(r) == len(h)]
     ci, si, wi = h.index("Instructions Executed"), h.index("# Samples"), h.index("L1 Wavefronts Shared")
     wx = h.index("L1 Wavefronts Shared Excessive")
     with tempfile.TemporaryDirectory() as td:

@@ -46,8 +46,14 @@ def main():
     heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
     if not heads:
         return
-    h = rows[heads[0]]
-    body = rows[heads[0] + 1: heads[1] - 1 if len(heads) > 1 else None]
+    # the SASS table of the first dmel_fused_kernel launch if there is one, else of the first launch
+    pick = 0
+    for n, hi in enumerate(heads):
+        if hi > 0 and any("dmel_fused_kernel" in c for c in rows[hi - 1]):
+            pick = n
+            break
+    h = rows[heads[pick]]
+    body = rows[heads[pick] + 1: heads[pick + 1] - 1 if len(heads) > pick + 1 else None]
     ci, si, srci = h.index("Instructions Executed"), h.index("# Samples"), h.index("Source")
     tot, samp, total = collections.Counter(), collections.Counter(), 0
     for r in body:
@@ -60,7 +66,7 @@ def main():
         samp[op] += s
         total += n
     div = frames or 1.0
-    print(f"-- dynamic SASS mix of the first launch: {total} warp instructions" + (f", {total / div:.1f} per frame" if frames else ""))
+    print(f"-- dynamic SASS mix of the fused launch: {total} warp instructions" + (f", {total / div:.1f} per frame" if frames else ""))
     for op, n in tot.most_common(28):
         print(f"   {op:12s} {n / div:12.1f}   stall samples {samp[op]}")
 
