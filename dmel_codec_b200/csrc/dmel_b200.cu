@@ -83,7 +83,7 @@ struct dmel_plan {
   int nnz = 0;
   int n_chan_pad = 0;  // n_mels rounded up to the channel-group size 32 / tile_frames
   size_t smem_bytes = 0;
-  mutable unsigned long long smem_opt_in = 0;  // bit per output MODE whose kernel already has its dynamic-smem limit raised
+  mutable bool smem_opt_in[128] = {};  // per output MODE: the kernel's dynamic shared-memory limit has been raised
   float* d_window = nullptr;
   float* d_window_pcm = nullptr;  // window / 32768: int16 PCM input needs no separate scaling pass
   float2* d_stage_tw = nullptr;
@@ -173,10 +173,11 @@ struct Launch {
   template <int NFFT, int TF, int OCC>
   cudaError_t launch() const {
     auto kern = dmel::dmel_fused_kernel<NFFT, TF, MODE, OCC>;
-    if (!(plan->smem_opt_in & (1ull << MODE))) {  // once per plan and output mode
+    static_assert(MODE >= 0 && MODE < 128, "MODE indexes dmel_plan::smem_opt_in");
+    if (!plan->smem_opt_in[MODE]) {  // once per plan and output mode
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
       if (e != cudaSuccess) return e;
-      plan->smem_opt_in |= 1ull << MODE;
+      plan->smem_opt_in[MODE] = true;
     }
     return launch_pdl(kern, dim3(grid), dim3(dmel::kThreads), plan->smem_bytes, st, *p);
   }
