@@ -474,3 +474,36 @@ def test_fused_forward_equals_encode_then_decode(d, name, n_bins):
     codes2, _ = tok.encode(wav)
     out2 = tok.encode_decode(wav)
     assert torch.equal(out2.codes, codes2) and torch.equal(out2.z, tok.decode(codes2))
+
+
+def _log_mel_float64(wav, cfg):
+    """The reference's chain (utils/spectrogram.py:41-81) evaluated in float64 on the same float32
+    window and filterbank: the yardstick for the rounding error of both float32 implementations."""
+    w = wav.squeeze(1).double() if wav.ndim == 3 else wav.double()
+    padded = torch.nn.functional.pad(w[:, None, :], (cfg.pad, cfg.pad), mode="reflect")[:, 0, :]
+    frames = padded.unfold(-1, cfg.n_fft, cfg.hop_length)
+    spec = torch.fft.rfft(frames * O.stft_window(cfg.win_length, cfg.n_fft).double(), dim=-1)
+    mag = torch.sqrt(spec.real.pow(2) + spec.imag.pow(2) + 1e-9).transpose(1, 2)
+    bank = torch.from_numpy(O.slaney_filterbank(cfg.sample_rate, cfg.n_fft, cfg.n_mels, cfg.f_min, cfg.f_max)).double()
+    return torch.log(torch.clamp(torch.matmul(bank, mag), min=1e-5))
+
+
+@pytest.mark.parametrize("name", ["cfg2_24k_128", "cfg5_44k_160"])
+def test_rounding_error_against_float64_is_no_worse_than_the_reference(d, name):
+    """Against a float64 evaluation, the kernel's log-mel error stays within twice the error of the
+    reference's own float32 path (torch.stft + matmul on the CPU) on speech-like and Gaussian audio."""
+    from dmel_codec_b200 import synth
+    kw = GOLDEN_GEOMETRY[name]
+    cfg = oracle_config(kw)
+    n = kw["sample_rate"] * 2 + 57
+    wav = torch.cat([synth.batch(range(750, 753), n, kw["sample_rate"], "speech"),
+                     synth.batch(range(753, 755), n, kw["sample_rate"], "noise")])
+    truth = _log_mel_float64(wav, cfg)
+    ref = O.log_mel(wav, cfg).double()
+    got = _transform(d, kw)(wav.cuda()).cpu().double()
+    scale = torch.clamp(truth.abs(), min=1.0)
+    err_ref = ((ref - truth).abs() / scale).max().item()
+    err_got = ((got - truth).abs() / scale).max().item()
+    print(f"{name}: max error vs float64  kernel {err_got:.2e}  reference float32 path {err_ref:.2e}")
+    assert err_got <= max(2.0 * err_ref, 5e-6), (err_got, err_ref)
+    assert err_got <= 1e-4
