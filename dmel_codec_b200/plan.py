@@ -82,11 +82,11 @@ class Plan:
     def __del__(self):
         h = getattr(self, "_handle", None)
         if h is not None and h.value:
+            self._handle = None  # at interpreter shutdown module globals (ctypes, _native) may already be gone
             try:
                 _native.load().dmel_plan_destroy(h)
             except Exception:
                 pass
-            self._handle = ctypes.c_void_p()
 
     def describe(self) -> dict:
         """Launch configuration the library chose for this geometry (diagnostics)."""

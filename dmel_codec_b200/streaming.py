@@ -46,6 +46,11 @@ class DMelStreamEncoder:
                                                        ctypes.byref(handle)))
         self._handle = handle
         self._count = ctypes.c_longlong(0)
+        self._count_ref = ctypes.byref(self._count)
+        mt = tokenizer.mel_transform
+        self._n_fft, self._hop = int(mt.n_fft), int(mt.hop_length)
+        self._pad = (self._n_fft - self._hop) // 2
+        self._seen = self._t_next = 0  # mirrors of the library's counters, for sizing the output
 
     def __del__(self):
         handle, self._handle = getattr(self, "_handle", None), None
@@ -57,11 +62,22 @@ class DMelStreamEncoder:
 
     def reset(self) -> None:
         _native.check(self._lib.dmel_stream_reset(self._handle))
+        self._seen = self._t_next = 0
+
+    def frames_after(self, n: int) -> int:
+        """Frames a push of ``n`` more samples per stream will emit (same arithmetic as
+        ``dmel_stream_pending``, kept on the Python side so a push is a single call into the library)."""
+        seen = self._seen + int(n)
+        if seen + self._pad < self._n_fft or seen <= self._pad:
+            return 0
+        return max((seen + self._pad - self._n_fft) // self._hop + 1 - self._t_next, 0)
 
     # ------------------------------------------------------------------
-    def push(self, chunk: torch.Tensor) -> torch.Tensor:
+    def push(self, chunk: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Append ``chunk`` ((n_streams, n) or (n,) float32, CUDA or CPU) and return
-        the codes of every frame that became complete: (n_streams, n_mels, k) uint8, k >= 0."""
+        the codes of every frame that became complete: (n_streams, n_mels, k) uint8, k >= 0.
+        ``out``: an optional (n_streams, n_mels, frames_after(n)) uint8 CUDA tensor to write into
+        (a latency-sensitive caller reuses its buffers)."""
         if chunk.ndim == 1:
             chunk = chunk[None, :]
         if chunk.shape[0] != self.n_streams:
@@ -74,13 +90,18 @@ class DMelStreamEncoder:
             chunk = chunk.to(self.device)
         n = chunk.shape[1]
         q = self.tok.quantizer
-        count = self._lib.dmel_stream_pending(self._handle, n, 0)
-        codes = torch.empty((self.n_streams, q.n_mels, count), dtype=torch.uint8, device=self.device)
+        count = self.frames_after(n)
+        if out is None:
+            out = torch.empty((self.n_streams, q.n_mels, count), dtype=torch.uint8, device=self.device)
+        elif out.shape != (self.n_streams, q.n_mels, count) or out.dtype != torch.uint8 or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous uint8 tensor of shape {(self.n_streams, q.n_mels, count)}")
         _native.check(self._lib.dmel_stream_push(
             self._handle, chunk.data_ptr(), n, chunk.stride(0) if self.n_streams > 1 else n, q.lo.data_ptr(),
-            q.scale().data_ptr(), q.n_bins, codes.data_ptr(), count, ctypes.byref(self._count),
+            q.scale().data_ptr(), q.n_bins, out.data_ptr(), count, self._count_ref,
             torch.cuda.current_stream(self.device).cuda_stream))
-        return codes
+        self._seen += n
+        self._t_next += count
+        return out
 
     def flush(self) -> torch.Tensor:
         """End of stream: emit the remaining frames (they use the reference's right-edge
@@ -90,5 +111,6 @@ class DMelStreamEncoder:
         codes = torch.empty((self.n_streams, q.n_mels, count), dtype=torch.uint8, device=self.device)
         _native.check(self._lib.dmel_stream_flush(
             self._handle, q.lo.data_ptr(), q.scale().data_ptr(), q.n_bins, codes.data_ptr(), count,
-            ctypes.byref(self._count), torch.cuda.current_stream(self.device).cuda_stream))
+            self._count_ref, torch.cuda.current_stream(self.device).cuda_stream))
+        self._seen = self._t_next = 0  # the library resets the stream after a flush
         return codes
