@@ -16,6 +16,13 @@
 //
 // HBM traffic per tile: hop*TF*4 B of new waveform in, n_mels*TF B of codes
 // out; constants come from L2.
+//
+// MODE (template parameter, bits kOut* / kIn* below) selects what a launch reads and writes: codes,
+// log-mel (float32 or bfloat16, optionally masked past the valid frames, optionally with per-channel
+// time sums), calibration min/max, near-edge counts, the bin centre of every code (the quantiser's
+// forward), int16 PCM input.  Tiles after a CTA's first are handed out by a global counter, and the
+// kernel takes part in programmatic dependent launch: plan-owned constants are loaded before
+// griddepcontrol.wait, caller memory is touched only after it.
 #pragma once
 #include <cstdint>
 #include <type_traits>
