@@ -366,6 +366,9 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
     for (int i = tid; i < LY::kFoldN; i += kThreads) s_fold[i] = p.fold_tw[i];
   }
   grid_dependency_wait();  // from here on: the caller's tensors (waveform, lengths, statistics, outputs, tile counter)
+  int tile = blockIdx.x;
+  TileInfo cur = describe(tile < p.n_tiles ? tile : 0);
+  if (tile < p.n_tiles) stage(cur, 0);  // the first tile leaves HBM while the statistics below are fetched
   if constexpr (kCodes) {
     for (int i = tid; i < p.n_chan_pad; i += kThreads) {
       const bool real = i < p.n_mels;
@@ -374,9 +377,6 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
       if constexpr (kDequant) s_step[i] = real ? p.q_step[i] : 0.f;
     }
   }
-  int tile = blockIdx.x;
-  TileInfo cur = describe(tile < p.n_tiles ? tile : 0);
-  if (tile < p.n_tiles) stage(cur, 0);
   __syncthreads();  // constants + barrier init visible
   // Tiles after the first are handed out by a global counter (lean variants), so the CTAs of the
   // grid finish within one tile of each other instead of one or two tiles apart.
