@@ -14,7 +14,7 @@ from ctypes import (POINTER, c_char_p, c_float, c_int, c_int32, c_longlong, c_ui
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DMEL_LIB") or os.path.join(_HERE, "libdmel_b200.so")  # DMEL_LIB: A/B builds
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = -1, -2, -3, -4
 
 # name -> (restype, argtypes); mirrors include/dmel_b200.h one to one
@@ -30,6 +30,8 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p]),
     "dmel_minmax_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_void_p,
                                 c_void_p, c_void_p, c_void_p]),
+    "dmel_logmel_minmax_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p]),
     "dmel_encode_u8": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_void_p,
                                c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
     "dmel_encode_decode_u8": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_void_p,

@@ -206,6 +206,7 @@ cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int gr
     case kOutLogmel: return launch_fused_mode<kOutLogmel>(plan, p, grid, st);
     case kOutLogmel | kOutBf16: return launch_fused_mode<kOutLogmel | kOutBf16>(plan, p, grid, st);
     case kOutStats: return launch_fused_mode<kOutStats>(plan, p, grid, st);
+    case kOutLogmel | kOutStats: return launch_fused_mode<kOutLogmel | kOutStats>(plan, p, grid, st);
     case kOutCodes | kOutLogmel: return launch_fused_mode<kOutCodes | kOutLogmel>(plan, p, grid, st);
     case kOutCodes | kOutEdge: return launch_fused_mode<kOutCodes | kOutEdge>(plan, p, grid, st);
     case kOutCodes | kOutLogmel | kOutEdge: return launch_fused_mode<kOutCodes | kOutLogmel | kOutEdge>(plan, p, grid, st);
@@ -562,6 +563,24 @@ int dmel_encode_u8(dmel_plan* plan, const float* wav_dev, long long n_rows, long
   p.logmel = logmel_dev;
   p.near_edge = near_edge_dev;
   p.edge_eps = edge_eps;
+  DeviceGuard guard(plan->device);
+  DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream));
+  return DMEL_OK;
+}
+
+int dmel_logmel_minmax_f32(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
+                           long long row_stride, const int32_t* lengths_dev, float* logmel_dev, float* min_dev,
+                           float* max_dev, void* stream) {
+  FusedParams p;
+  int grid = 0;
+  int rc = prepare_fused(plan, wav_dev, n_rows, n_samples, row_stride, &p, &grid);
+  if (rc != DMEL_OK) return rc;
+  if (!logmel_dev || !min_dev || !max_dev) return fail(DMEL_ERR_INVALID, "logmel_dev / min_dev / max_dev is null");
+  if (n_rows == 0) return DMEL_OK;
+  p.lengths = lengths_dev;
+  p.logmel = logmel_dev;
+  p.run_min = min_dev;
+  p.run_max = max_dev;
   DeviceGuard guard(plan->device);
   DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream));
   return DMEL_OK;

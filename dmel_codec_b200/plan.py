@@ -140,6 +140,20 @@ class Plan:
             self._handle, rows.data_ptr(), b, n, rows.stride(0) if b > 1 else n, len_ptr[0],
             run_min.data_ptr(), run_max.data_ptr(), _stream_ptr(rows.device)))
 
+    def logmel_minmax(self, wav: torch.Tensor, lengths: Optional[torch.Tensor], run_min: torch.Tensor,
+                      run_max: torch.Tensor) -> torch.Tensor:
+        """Log-mel of every frame, and the running per-channel min / max over the valid ones, one launch."""
+        _require_cuda(wav, "audio")
+        rows = as_rows(wav)
+        b, n = rows.shape
+        t = self._frames_or_raise(n)
+        out = torch.empty((b, self.n_mels, t), dtype=torch.float32, device=rows.device)
+        len_ptr = self._lengths_ptr(lengths, b, rows.device)
+        _native.check(_native.load().dmel_logmel_minmax_f32(
+            self._handle, rows.data_ptr(), b, n, rows.stride(0) if b > 1 else n, len_ptr[0], out.data_ptr(),
+            run_min.data_ptr(), run_max.data_ptr(), _stream_ptr(rows.device)))
+        return out
+
     # -- waveform -> codes, fused --------------------------------------------
     def encode(self, wav: torch.Tensor, lengths: Optional[torch.Tensor], lo: torch.Tensor, scale: torch.Tensor,
                n_bins: int, *, return_logmel: bool = False, near_edge: Optional[torch.Tensor] = None,

@@ -189,6 +189,14 @@ class DMelTokenizer(nn.Module):
         self._plan(audios.device).update_minmax(audios, self._flat_lengths(audio_lengths), q.lo, q.hi)
 
     @torch.no_grad()
+    def update_stats_keep_mel(self, audios: Tensor, audio_lengths: Optional[Tensor] = None) -> Tensor:
+        """One calibration step that also returns the batch's log-mel (one launch), so that the encode pass of a
+        calibrate-then-encode job can quantise the stored tensor instead of running the STFT again."""
+        q = self.quantizer
+        q._invalidate()
+        return self._plan(audios.device).logmel_minmax(audios, self._flat_lengths(audio_lengths), q.lo, q.hi)
+
+    @torch.no_grad()
     def calibrate(self, batches: Iterable, group=None) -> Tuple[Tensor, Tensor]:
         """Reset, scan ``batches`` (audios or (audios, audio_lengths)), then
         all-reduce across ranks.  Returns (lo, hi)."""

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DMEL_ABI_VERSION 6
+#define DMEL_ABI_VERSION 7
 
 #define DMEL_OK 0
 #define DMEL_ERR_INVALID (-1)     /* bad argument (shape, null pointer, L <= reflect pad ...) */
@@ -94,6 +94,14 @@ int dmel_logmel_masked(dmel_plan* plan, const float* wav_dev, long long n_rows, 
 int dmel_minmax_f32(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
                     long long row_stride, const int32_t* lengths_dev,
                     float* min_dev, float* max_dev, void* stream);
+
+/* dmel_logmel_f32 and dmel_minmax_f32 in one launch: writes the log-mel of every frame and folds the
+ * valid ones into the running per-channel min / max.  With the log-mel of a shard kept in HBM the
+ * calibrate-then-encode job of a dataset needs the STFT only once: pass 2 is dmel_quantize_u8 over the
+ * stored tensor (bit-identical to the fused encode, which quantises the same float32 values). */
+int dmel_logmel_minmax_f32(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
+                           long long row_stride, const int32_t* lengths_dev, float* logmel_dev,
+                           float* min_dev, float* max_dev, void* stream);
 
 /* waveform -> uint8 dMel codes, fused.  code = clamp(floor((x - lo_c) * scale_c), 0, K-1)
  * with scale_c = K / (hi_c - lo_c) supplied by the caller (float32, n_mels each).

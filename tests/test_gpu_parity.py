@@ -507,3 +507,24 @@ def test_rounding_error_against_float64_is_no_worse_than_the_reference(d, name):
     print(f"{name}: max error vs float64  kernel {err_got:.2e}  reference float32 path {err_ref:.2e}")
     assert err_got <= max(2.0 * err_ref, 5e-6), (err_got, err_ref)
     assert err_got <= 1e-4
+
+
+def test_single_transform_calibrate_encode_equals_two_pass_job(d):
+    """distributed.calibrate_encode_sharded (log-mel stored by the calibration pass, stand-alone quantiser as
+    pass 2) gives the statistics and the codes of calibrate_sharded + encode_sharded, bit for bit."""
+    from dmel_codec_b200 import distributed as D, synth
+    kw = GOLDEN_GEOMETRY["cfg1_16k_80"]
+    n = 16000 * 2 + 101
+    pool = synth.batch(range(760, 772), n, 16000, "speech").cuda()
+    lengths = torch.randint(2000, n, (12,), generator=torch.Generator().manual_seed(9)).cuda()
+    for with_lengths in (False, True):
+        load = (lambda ids: (pool[list(ids)], lengths[list(ids)])) if with_lengths else (lambda ids: pool[list(ids)])
+        a, b = _tokenizer(d, kw, 16), _tokenizer(d, kw, 16)
+        D.calibrate_sharded(a, 12, load, 5)
+        want = list(D.encode_sharded(a, 12, load, 5))
+        got = list(D.calibrate_encode_sharded(b, 12, load, 5))
+        assert torch.equal(a.quantizer.lo, b.quantizer.lo) and torch.equal(a.quantizer.hi, b.quantizer.hi)
+        assert len(want) == len(got) == 3
+        for (ids_w, codes_w, len_w), (ids_g, codes_g, len_g) in zip(want, got):
+            assert list(ids_w) == list(ids_g) and torch.equal(codes_w, codes_g)
+            assert (len_w is None and len_g is None) or torch.equal(len_w, len_g)
