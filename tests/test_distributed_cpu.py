@@ -73,3 +73,70 @@ def test_sharded_calibration_allreduce_is_bit_identical(tmp_path):
     assert sum(g["n"] for g in got) == n_utts
     for g in got:
         assert torch.equal(g["lo"], lo) and torch.equal(g["hi"], hi)
+
+
+class _OracleTokenizer:
+    """CPU stand-in with the three members distributed.calibrate_encode_sharded uses; the transform and the
+    quantiser are the oracle's (the CUDA kernels cannot run here).  Under test: the host logic of the
+    single-transform job under world_size 2."""
+
+    def __init__(self, kw, n_bins):
+        import dmel_codec_b200 as d
+        from oracle import dmel_oracle as O
+        self.O, self.cfg, self.n_bins = O, oracle_config(kw), n_bins
+        self.hop_length = kw["hop_length"]
+        self.quantizer = d.DMelQuantizer(kw["n_mels"], n_bins)
+        self.quantizer.encode = lambda mel: O.dmel_encode(mel, self.quantizer.lo, self.quantizer.hi, n_bins)
+
+    def update_stats_keep_mel(self, audios, lengths=None):
+        mel = self.O.log_mel(audios, self.cfg)
+        n_valid = None if lengths is None else self.O.valid_frames(lengths, self.cfg.hop_length)
+        lo, hi = self.O.calibrate_minmax(mel, n_valid)
+        self.quantizer.set_stats(torch.minimum(self.quantizer.lo, lo), torch.maximum(self.quantizer.hi, hi))
+        return mel
+
+
+def _lengths_of(ids):
+    return torch.tensor([6000 + 500 * (i % 4) for i in ids])
+
+
+def _job_worker(rank, world_size, port, n_utts, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        from dmel_codec_b200 import synth
+        tok = _OracleTokenizer(GOLDEN_GEOMETRY["cfg1_16k_80"], 16)
+
+        def load(ids):
+            lengths = _lengths_of(ids)
+            return synth.batch(ids, 8000, 16000, "speech", lengths=lengths.tolist()), lengths
+
+        out = [(list(ids), codes, code_lengths) for ids, codes, code_lengths in D.calibrate_encode_sharded(tok, n_utts, load, 3)]
+        torch.save(out, os.path.join(out_dir, f"job{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_single_transform_job_under_two_ranks(tmp_path):
+    """calibrate_encode_sharded on 2 ranks == tokenising the whole set in one process with dataset-wide
+    statistics: every utterance once, in shard order, codes zero past the valid frames."""
+    from dmel_codec_b200 import synth
+    from oracle import dmel_oracle as O
+    n_utts, world_size = 10, 2
+    mp.spawn(_job_worker, args=(world_size, _free_port(), n_utts, str(tmp_path)), nprocs=world_size, join=True)
+    kw = GOLDEN_GEOMETRY["cfg1_16k_80"]
+    cfg = oracle_config(kw)
+    ids = list(range(n_utts))
+    lengths = _lengths_of(ids)
+    mel = O.log_mel(synth.batch(ids, 8000, 16000, "speech", lengths=lengths.tolist()), cfg)
+    n_valid = O.valid_frames(lengths, cfg.hop_length)
+    lo, hi = O.calibrate_minmax(mel, n_valid)
+    want = O.dmel_encode(mel, lo, hi, 16)
+    want = want * (torch.arange(want.shape[2])[None, None, :] < n_valid[:, None, None])
+    seen = []
+    for r in range(world_size):
+        for batch_ids, codes, code_lengths in torch.load(tmp_path / f"job{r}.pt"):
+            assert torch.equal(codes, want[batch_ids]) and torch.equal(code_lengths, n_valid[batch_ids])
+            seen += batch_ids
+    assert seen == ids
