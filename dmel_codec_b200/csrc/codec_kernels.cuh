@@ -6,33 +6,12 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "fastdiv.cuh"
+
 namespace dmel {
 
 constexpr int kStreamThreads = 256;
 constexpr int kStreamUnroll = 4;  // groups of 4 elements per thread per trip
-
-// Exact unsigned division of e < 2^31 by a fixed d via one multiply-high and a shift
-// (round-up method: mul = floor(2^(31+s)/d) + 1 with s = ceil(log2 d)); the flat-indexed
-// kernels below need (e / T) and (row % M) per 4 elements and were issue-bound on the
-// hardware divide sequence.
-struct FastDiv {
-  unsigned mul, shift, d;
-  __host__ static FastDiv make(unsigned d) {
-    FastDiv f;
-    f.d = d;
-    if (d <= 1) {
-      f.mul = 0;
-      f.shift = 0;
-      return f;
-    }
-    unsigned s = 0;
-    while ((1ull << s) < d) ++s;
-    f.mul = (unsigned)(((1ull << (31 + s)) / d) + 1);
-    f.shift = s - 1;
-    return f;
-  }
-  __device__ __forceinline__ unsigned div(unsigned e) const { return d <= 1 ? e : (__umulhi(e, mul) >> shift); }
-};
 
 // ---------------------------------------------------------------------------
 // codes (uint8) -> bin centres (float32) by table lookup.  The table is built

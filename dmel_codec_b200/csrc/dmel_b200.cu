@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 
 #include "../../include/dmel_b200.h"
+#include "fused_variants.h"
+#include "launch_util.cuh"
 #include "logmel_kernel.cuh"
 #include "codec_kernels.cuh"
 
@@ -41,25 +43,7 @@ int fail(int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                   \
   } while (0)
 
-// Every kernel of this library is launched with the programmatic-stream-serialisation attribute: when the
-// previous operation of the stream is one of our kernels (they all execute griddepcontrol.launch_dependents),
-// the launch latency and the plan-constant prologue of this one overlap its tail; each kernel executes
-// griddepcontrol.wait before it touches caller memory.  DMEL_NO_PDL=1 gives ordinary launches.
-template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  static const bool pdl = std::getenv("DMEL_NO_PDL") == nullptr;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
-}
+using dmel::launch_pdl;
 
 template <typename T>
 cudaError_t upload(T** dev, const std::vector<T>& host) {
@@ -83,12 +67,12 @@ struct dmel_plan {
   int nnz = 0;
   int n_chan_pad = 0;  // n_mels rounded up to the channel-group size 32 / tile_frames
   size_t smem_bytes = 0;
-  mutable bool smem_opt_in[128] = {};  // per output MODE: the kernel's dynamic shared-memory limit has been raised
+  const dmel::VariantOps* variant = nullptr;  // the kernel variant chosen for this geometry
   float* d_window = nullptr;
   float* d_window_pcm = nullptr;  // window / 32768: int16 PCM input needs no separate scaling pass
   float2* d_stage_tw = nullptr;
   float2* d_fold_tw = nullptr;
-  int2* d_chan = nullptr;
+  int4* d_chan = nullptr;
   float* d_weights = nullptr;
   // dynamic tile scheduling: kSchedSlots {next tile, finished CTAs} pairs, zero between launches; launches rotate
   // through them so that launches of one plan that overlap on different streams do not share a counter
@@ -109,84 +93,12 @@ namespace {
 
 using dmel::FusedParams;
 
-// The kernel variants this build carries: (n_fft, frames per tile, CTAs per SM).
-struct Variant {
-  int n_fft, tf, occ;
-};
-constexpr Variant kVariants[] = {{1024, 8, 3}, {1024, 16, 2}, {1024, 8, 2}, {1024, 16, 1}, {1024, 8, 1},
-                                 {2048, 8, 2}, {2048, 16, 1}, {2048, 8, 1}};
-
-// calls f.template operator()<NFFT, TF, OCC>() for the variant (compile-time dispatch)
-template <typename F>
-auto dispatch_variant(int n_fft, int tf, int occ, F&& f) {
-  if (n_fft == 1024) {
-    if (tf == 8 && occ == 3) return f.template operator()<1024, 8, 3>();
-    if (tf == 16) return occ == 2 ? f.template operator()<1024, 16, 2>() : f.template operator()<1024, 16, 1>();
-    return occ == 2 ? f.template operator()<1024, 8, 2>() : f.template operator()<1024, 8, 1>();
-  }
-  if (tf == 8 && occ == 2) return f.template operator()<2048, 8, 2>();
-  return tf == 16 ? f.template operator()<2048, 16, 1>() : f.template operator()<2048, 8, 1>();
-}
+// The kernel variants this build carries, most CTAs per SM first (one translation unit each: fused_variant.cu).
+const dmel::VariantOps* const kVariants[] = {
+    &dmel::kVariant_1024_8_3, &dmel::kVariant_1024_16_2, &dmel::kVariant_1024_8_2, &dmel::kVariant_1024_16_1,
+    &dmel::kVariant_1024_8_1, &dmel::kVariant_2048_8_2,  &dmel::kVariant_2048_16_1, &dmel::kVariant_2048_8_1};
 
 constexpr unsigned kSchedSlots = 64;
-
-struct FillOffsets {
-  FusedParams* p;
-  template <int NFFT, int TF, int OCC>
-  int operator()() const {
-    using LY = dmel::FusedLayout<NFFT, TF, OCC>;
-    p->off_mags = (int)LY::mags_off();
-    p->off_wave = (int)LY::wave_off();
-    p->off_window = (int)LY::window_off(p->wave_len);
-    p->off_fold = (int)LY::fold_off(p->wave_len);
-    p->off_chan = (int)LY::chan_off(p->wave_len);
-    p->off_weights = (int)LY::weights_off(p->wave_len, p->n_chan_pad);
-    p->off_perchan = (int)LY::perchan_off(p->wave_len, p->n_chan_pad, p->nnz);
-    p->off_bars = (int)LY::bar_off(p->wave_len, p->n_chan_pad, p->nnz);
-    return 0;
-  }
-};
-
-struct SmemNeed {
-  int wave_len, n_chan, nnz;
-  template <int NFFT, int TF, int OCC>
-  size_t operator()() const {
-    return dmel::FusedLayout<NFFT, TF, OCC>::total(wave_len, n_chan, nnz);
-  }
-};
-
-template <int MODE>
-struct Launch {
-  const dmel_plan* plan;
-  const FusedParams* p;
-  int grid;
-  cudaStream_t st;
-  template <int NFFT, int TF, int OCC>
-  cudaError_t operator()() const {
-    constexpr bool kLeanVariant = OCC == 3 || (NFFT == 2048 && OCC == 2);
-    if constexpr ((MODE & dmel::kInPcm16) != 0 && !kLeanVariant) {
-      return cudaErrorNotSupported;  // int16 input is built for the register-lean variants only
-    } else {
-      return launch<NFFT, TF, OCC>();
-    }
-  }
-  template <int NFFT, int TF, int OCC>
-  cudaError_t launch() const {
-    auto kern = dmel::dmel_fused_kernel<NFFT, TF, MODE, OCC>;
-    static_assert(MODE >= 0 && MODE < 128, "MODE indexes dmel_plan::smem_opt_in");
-    if (!plan->smem_opt_in[MODE]) {  // once per plan and output mode
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes);
-      if (e != cudaSuccess) return e;
-      plan->smem_opt_in[MODE] = true;
-    }
-    return launch_pdl(kern, dim3(grid), dim3(dmel::kThreads), plan->smem_bytes, st, *p);
-  }
-};
-
-template <int MODE>
-cudaError_t launch_fused_mode(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st) {
-  return dispatch_variant(plan->n_fft, plan->tile_frames, plan->ctas_per_sm, Launch<MODE>{plan, &p, grid, st});
-}
 
 cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st,
                              bool bf16_logmel = false, bool pcm16 = false) {
@@ -199,19 +111,7 @@ cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int gr
   if (bf16_logmel) mode |= kOutBf16;
   if (pcm16) mode |= kInPcm16;
   if (p.dequant) mode |= kOutDequant;
-  switch (mode) {
-    case kOutCodes: return launch_fused_mode<kOutCodes>(plan, p, grid, st);
-    case kOutCodes | kInPcm16: return launch_fused_mode<kOutCodes | kInPcm16>(plan, p, grid, st);
-    case kOutCodes | kOutDequant: return launch_fused_mode<kOutCodes | kOutDequant>(plan, p, grid, st);
-    case kOutLogmel: return launch_fused_mode<kOutLogmel>(plan, p, grid, st);
-    case kOutLogmel | kOutBf16: return launch_fused_mode<kOutLogmel | kOutBf16>(plan, p, grid, st);
-    case kOutStats: return launch_fused_mode<kOutStats>(plan, p, grid, st);
-    case kOutLogmel | kOutStats: return launch_fused_mode<kOutLogmel | kOutStats>(plan, p, grid, st);
-    case kOutCodes | kOutLogmel: return launch_fused_mode<kOutCodes | kOutLogmel>(plan, p, grid, st);
-    case kOutCodes | kOutEdge: return launch_fused_mode<kOutCodes | kOutEdge>(plan, p, grid, st);
-    case kOutCodes | kOutLogmel | kOutEdge: return launch_fused_mode<kOutCodes | kOutLogmel | kOutEdge>(plan, p, grid, st);
-    default: return cudaErrorInvalidValue;
-  }
+  return plan->variant->launch(mode, p, grid, plan->smem_bytes, st);
 }
 
 // Banded form of the (n_mels, n_freq) filterbank the kernel reads: per channel the contiguous
@@ -219,10 +119,10 @@ cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int gr
 // loads).  `group` adjacent channels are evaluated side by side in one warp, so their spans are
 // zero-padded to one common length (a multiple of 4, at least 4) and phantom channels complete
 // the last group; the bin loop is then uniform across the warp.
-void band_filterbank(const float* basis, int n_mels, int n_freq, int group, std::vector<int2>* chan,
+void band_filterbank(const float* basis, int n_mels, int n_freq, int group, std::vector<int4>* chan,
                      std::vector<float>* weights) {
   const int n_pad = (n_mels + group - 1) / group * group;
-  chan->assign(n_pad, make_int2(4 << 16, 0));
+  chan->assign(n_pad, make_int4(0, 0, 16, 0));
   weights->clear();
   std::vector<int> first(n_pad, 0), last(n_pad, -1);
   for (int m = 0; m < n_mels; ++m) {
@@ -242,7 +142,8 @@ void band_filterbank(const float* basis, int n_mels, int n_freq, int group, std:
     const int pitch = n_freq + 3;  // FusedLayout::kMagPitch, a multiple of 4
     for (int m = g; m < g + group; ++m) {
       first[m] = std::min(first[m], pitch - count);  // keep the padded span inside the frame's row
-      (*chan)[m] = make_int2(first[m] | (count << 16), (int)weights->size());
+      // the integer half of dmel::ChanRec, in bytes: {first bin, first weight, span length, -}
+      (*chan)[m] = make_int4(first[m] * 4, (int)weights->size() * 4, count * 4, 0);
       for (int i = 0; i < count; ++i) {
         const int f = first[m] + i;
         weights->push_back((m < n_mels && f >= 0 && f <= last[m]) ? basis[(size_t)m * n_freq + f] : 0.f);
@@ -316,7 +217,9 @@ int prepare_window(dmel_plan* plan, const float* wav, long long n_rows, long lon
   p->kmax = 0.f;
   if (plan->d_sched && !std::getenv("DMEL_STATIC_TILES")) p->sched = plan->d_sched + 2 * (plan->sched_turn++ % kSchedSlots);
   if (const char* dbg = std::getenv("DMEL_DEBUG_SKIP")) p->debug_skip = std::atoi(dbg);  // ablation timing only
-  dispatch_variant(plan->n_fft, plan->tile_frames, plan->ctas_per_sm, FillOffsets{p});
+  p->by_tiles_per_row = dmel::FastDiv::make((unsigned)tiles_per_row);
+  p->by_hop = dmel::FastDiv::make((unsigned)plan->hop);
+  plan->variant->fill_offsets(p);
   *grid = (int)std::max<long long>(1, std::min<long long>(n_tiles, (long long)plan->sm_count * plan->ctas_per_sm));
   return DMEL_OK;
 }
@@ -375,11 +278,20 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
     cudaGetLastError();
     return fail(DMEL_ERR_NO_DEVICE, "no CUDA device visible; dmel_b200 has no CPU path");
   }
+  for (size_t i = 0; i < (size_t)n_mels * (n_fft / 2 + 1); ++i)
+    if (!std::isfinite(mel_basis_host[i])) return fail(DMEL_ERR_INVALID, "mel_basis[%zu] is not finite", i);
+
   dmel_plan* plan = new (std::nothrow) dmel_plan();
   if (!plan) return fail(DMEL_ERR_INVALID, "out of host memory");
-  DMEL_CUDA(cudaGetDevice(&plan->device));
-  DMEL_CUDA(cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, plan->device));
-  DMEL_CUDA(cudaDeviceGetAttribute(&plan->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, plan->device));
+  int max_sm_smem = 0;
+  cudaError_t e = cudaGetDevice(&plan->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, plan->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&plan->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, plan->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, plan->device);
+  if (e != cudaSuccess) {
+    delete plan;
+    return fail(DMEL_ERR_CUDA, "device query failed: %s", cudaGetErrorString(e));
+  }
   plan->n_fft = n_fft;
   plan->hop = hop_length;
   plan->n_mels = n_mels;
@@ -387,37 +299,30 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
   plan->pad_inner = (n_fft - hop_length) / 2;  // reference utils/spectrogram.py:58
   plan->pad_outer = center ? n_fft / 2 : 0;
 
-  for (size_t i = 0; i < (size_t)n_mels * (n_fft / 2 + 1); ++i)
-    if (!std::isfinite(mel_basis_host[i])) {
-      delete plan;
-      return fail(DMEL_ERR_INVALID, "mel_basis[%zu] is not finite", i);
-    }
-
   // pick the first kernel variant (most CTAs per SM first) whose shared memory fits; DMEL_OCC=<n>
   // pins the CTAs-per-SM choice (experiments)
-  int max_sm_smem = 0;
-  DMEL_CUDA(cudaDeviceGetAttribute(&max_sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, plan->device));
   const char* occ_env = std::getenv("DMEL_OCC");
   const int occ_pin = occ_env ? std::atoi(occ_env) : 0;
-  std::vector<int2> chan;
+  std::vector<int4> chan;
   std::vector<float> weights;
-  for (const Variant& v : kVariants) {
-    if (v.n_fft != n_fft || (occ_pin && v.occ != occ_pin)) continue;
-    band_filterbank(mel_basis_host, n_mels, n_fft / 2 + 1, 32 / v.tf, &chan, &weights);
-    const int wave_len = ((v.tf - 1) * hop_length + n_fft + 7) / 8 * 8;  // whole 16-byte units of float and of int16
-    const size_t need = dispatch_variant(v.n_fft, v.tf, v.occ, SmemNeed{wave_len, (int)chan.size(), (int)weights.size()});
-    const size_t limit = std::min<size_t>((size_t)max_sm_smem / v.occ - 1024, (size_t)plan->max_smem);  // 1 KB/CTA reserved
+  for (const dmel::VariantOps* v : kVariants) {
+    if (v->n_fft != n_fft || (occ_pin && v->occ != occ_pin)) continue;
+    band_filterbank(mel_basis_host, n_mels, n_fft / 2 + 1, 32 / v->tf, &chan, &weights);
+    const int wave_len = ((v->tf - 1) * hop_length + n_fft + 7) / 8 * 8;  // whole 16-byte units of float and of int16
+    const size_t need = v->smem_need(wave_len, (int)chan.size(), (int)weights.size());
+    const size_t limit = std::min<size_t>((size_t)max_sm_smem / v->occ - 1024, (size_t)plan->max_smem);  // 1 KB/CTA reserved
     if (need <= limit) {
-      plan->tile_frames = v.tf;
+      plan->variant = v;
+      plan->tile_frames = v->tf;
       plan->wave_len = wave_len;
       plan->smem_bytes = need;
-      plan->ctas_per_sm = v.occ;
+      plan->ctas_per_sm = v->occ;
       plan->nnz = (int)weights.size();
       plan->n_chan_pad = (int)chan.size();
       break;
     }
   }
-  if (!plan->tile_frames) {
+  if (!plan->variant) {
     const int max_smem = plan->max_smem;
     delete plan;
     return fail(DMEL_ERR_UNSUPPORTED, "geometry needs more than %d bytes of shared memory per CTA", max_smem);
@@ -439,7 +344,7 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
   }
   std::vector<float> window_pcm(window);
   for (float& w : window_pcm) w *= 1.0f / 32768.0f;  // exact: a power of two
-  cudaError_t e = upload(&plan->d_window, window);
+  e = upload(&plan->d_window, window);
   if (e == cudaSuccess) e = upload(&plan->d_window_pcm, window_pcm);
   if (e == cudaSuccess) e = upload(&plan->d_stage_tw, stage_tw);
   if (e == cudaSuccess) e = upload(&plan->d_fold_tw, fold_tw);
@@ -620,7 +525,7 @@ int dmel_encode_pcm16_u8(dmel_plan* plan, const int16_t* wav_dev, long long n_ro
   if (rc != DMEL_OK) return rc;
   if ((rc = check_bins(n_bins)) != DMEL_OK) return rc;
   if (!lo_dev || !scale_dev || !codes_dev) return fail(DMEL_ERR_INVALID, "lo_dev / scale_dev / codes_dev is null");
-  if (!(plan->ctas_per_sm == 3 || (plan->n_fft == 2048 && plan->ctas_per_sm == 2)))
+  if (!plan->variant->lean)
     return fail(DMEL_ERR_UNSUPPORTED, "int16 input needs the register-lean kernel variant, which does not fit this geometry");
   if (n_rows == 0) return DMEL_OK;
   p.window = plan->d_window_pcm;

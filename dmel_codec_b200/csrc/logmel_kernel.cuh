@@ -2,20 +2,25 @@
 //
 // One CTA owns tiles of TF consecutive frames of one utterance row:
 //   1. the (TF-1)*hop + n_fft samples of the NEXT tile are pulled into shared
-//      memory by one bulk async copy (cp.async.bulk + mbarrier, double
-//      buffered) while the current tile computes; row ends, where the
-//      reference reflect-pads (utils/spectrogram.py:58-62), are staged by
-//      ordinary reflect-indexed loads.  The 4x frame overlap is re-read on
-//      chip, never from HBM;
+//      memory by one bulk async copy (cp.async.bulk + mbarrier) while the
+//      current tile computes; row ends, where the reference reflect-pads
+//      (utils/spectrogram.py:58-62), are staged by ordinary reflect-indexed
+//      loads.  The 4x frame overlap is re-read on chip, never from HBM;
 //   2. each warp turns frames into magnitudes with the register FFT of
 //      fft_core.cuh (window multiply on load, torch.stft at :64-75, magnitude
-//      at :76) and drops them in a [frame][bin] shared tile;
+//      at :76).  With one frame per warp and tile (TF == 8) the magnitudes
+//      overwrite the warp's own transpose tile, so they need no storage of
+//      their own;
 //   3. the banded mel filterbank (:78), log(clamp(.,1e-5)) (:38-39) and the
 //      per-channel bin quantiser run with one lane per
 //      frame, and only codes / log-mel / min-max leave the SM.
 //
 // HBM traffic per tile: hop*TF*4 B of new waveform in, n_mels*TF B of codes
 // out; constants come from L2.
+//
+// Tile bookkeeping (which row, which frames, what to copy) is done by ONE
+// thread per CTA, which leaves the description of the next tile in a shared
+// slot; divisions by run-time constants are multiply-high (fastdiv.cuh).
 //
 // MODE (template parameter, bits kOut* / kIn* below) selects what a launch reads and writes: codes,
 // log-mel (float32 or bfloat16, optionally masked past the valid frames, optionally with per-channel
@@ -29,6 +34,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include "fastdiv.cuh"
 #include "fft_core.cuh"
 
 namespace dmel {
@@ -46,6 +52,16 @@ constexpr int kOutBf16 = 16;  // the log-mel output tensor is bfloat16 (needs kO
 constexpr int kOutDequant = 64;  // also write the bin centre of every code, float32 (needs kOutCodes): the quantiser's forward
 constexpr int kInPcm16 = 32;  // the waveform is int16 PCM (x / 32768 is folded into the window taps); lean variants only
 
+// one filterbank channel as the mel phase reads it (32 bytes in shared memory: two 16-byte loads)
+struct ChanRec {
+  int x_off;     // byte offset of the first bin of the span inside a magnitude row (multiple of 16)
+  int w_off;     // byte offset of the span's weights inside the banded weight array (multiple of 16)
+  int span;      // bytes of magnitudes in the span (multiple of 16, equal within a channel group, >= 16)
+  int pad;
+  float a, b, c, d;  // quantiser {lo, scale, step, -} when writing codes; running {min, max} when calibrating
+};
+static_assert(sizeof(ChanRec) == 32, "two 16-byte loads");
+
 struct FusedParams {
   const float* wav;         // (B, row_stride) device; int16_t with kInPcm16
   long long row_stride;     // samples between rows
@@ -61,12 +77,14 @@ struct FusedParams {
   int pad_outer;            // n_fft/2 when center=True, else 0
   int n_mels;
   int n_chan_pad;           // n_mels rounded up to the channel-group size 32/TF
-  int wave_len;             // staged samples per tile (multiple of 4)
+  int wave_len;             // staged samples per tile (multiple of 8)
   int nnz;                  // banded weights
+  FastDiv by_tiles_per_row; // tile -> row
+  FastDiv by_hop;           // length -> valid frames
   const float* window;      // (n_fft)
   const float2* stage_tw;   // n_fft 1024: [16][32] W_512^{k1*n2}; n_fft 2048: [32][32] W_1024^{k1*n2}
   const float2* fold_tw;    // [n_fft/4 + 1]: W_{n_fft}^k
-  const int2* chan;         // (n_chan_pad) {first bin | count << 16 (both mult. of 4, count equal within a group), weight offset}
+  const int4* chan;         // (n_chan_pad) {x_off, w_off, span, 0}: the integer half of ChanRec
   const float* weights;
   const int* lengths;       // valid samples per row, or null
   float* logmel;            // (B, M, T)            [kOutLogmel]; __nv_bfloat16 with kOutBf16
@@ -81,14 +99,20 @@ struct FusedParams {
   float kmax;               // float(n_bins - 1)
   // byte offsets of the shared-memory regions (FusedLayout, filled in by the host so the kernel
   // does no layout arithmetic)
-  int off_mags, off_wave, off_window, off_fold, off_chan, off_weights, off_perchan, off_bars;
+  int off_mags, off_wave, off_window, off_fold, off_rec, off_weights, off_bars;
   int* sched;               // {next dynamic tile, finished CTAs}, both 0 between launches; null = static tile walk
-  int debug_skip;           // diagnostics (env DMEL_DEBUG_SKIP): 1 skip the FFT phase, 2 skip mel/epilogue, 4 skip staging
+  int debug_skip;           // diagnostics (env DMEL_DEBUG_SKIP, builds with -DDMEL_ABLATION only): 1 skip the FFT phase, 2 skip mel/epilogue, 4 skip staging
   float* run_min;           // (M) running min, updated in place [kOutStats]
   float* run_max;           // (M)
   unsigned long long* near_edge;  // [kOutEdge]
   float edge_eps;
 };
+
+#ifdef DMEL_ABLATION
+#define DMEL_SKIP(p, bit) (((p).debug_skip & (bit)) != 0)
+#else
+#define DMEL_SKIP(p, bit) false
+#endif
 
 // index into the unpadded row for position j of the (doubly) reflect-padded row
 __device__ __forceinline__ int reflect_src(int j, int n, int pad_inner, int pad_outer) {
@@ -104,12 +128,17 @@ __device__ __forceinline__ int reflect_src(int j, int n, int pad_inner, int pad_
   return j;
 }
 
+// Order-preserving integer atomics on float bit patterns.  The branch is on the SIGN BIT, so -0.0f takes the
+// unsigned path (as a plain `v >= 0` would not: its pattern 0x80000000 is INT_MIN and would beat every negative
+// minimum); NaN is dropped, it has no place in an order.
 __device__ __forceinline__ void atomic_min_float(float* addr, float v) {
-  if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  if (v != v) return;
+  if (__float_as_int(v) >= 0) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
   else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
-  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  if (v != v) return;
+  if (__float_as_int(v) >= 0) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
@@ -122,29 +151,48 @@ __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepco
 
 // ---- mbarrier + bulk async copy (TMA engine, 1-D) ----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// ---- explicit shared-space accesses on 32-bit addresses -------------------------
+// The mel phase and the tile slot use these instead of generic pointers: one cvta at kernel entry, immediate
+// offsets afterwards, nothing for the compiler to re-derive per use.
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int4 lds_i4(uint32_t a) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_i4(uint32_t a, int4 v) {
+  asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_f2(uint32_t a, float x, float y) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
 }
 
 // OCC = CTAs per SM the instantiation is built for.  OCC == 3 (n_fft 1024, TF 8 only) trades
@@ -159,37 +207,39 @@ struct FusedLayout {
   static constexpr int kWaveBufs = (OCC == 3 || kSplit2048) ? 1 : 2;
   static constexpr bool kWindowInSmem = NFFT == 2048 || OCC == 3;
   static constexpr int kBins = NFFT / 2 + 1;
-  // row pitch 516 / 1028 floats: a multiple of 4 so a lane can fetch four bins of its frame with
+  static constexpr bool kTile512 = NFFT == 1024 || kSplit2048;
+  // One frame per warp and tile: the frame's magnitudes replace the warp's transpose tile once the
+  // second FFT pass has read it, and the tiles double as the [frame][bin] magnitude array.
+  static constexpr bool kMagsInTiles = TF == kWarps && kTile512;
+  // Magnitude row pitch in floats: a multiple of 4 so a lane can fetch four bins of its frame with
   // one LDS.128, and == 4 (mod 32) so the eight lanes of a quarter-warp (eight frames) cover all
   // 32 banks.  The host keeps every padded span inside its row.
-  static constexpr int kMagPitch = kBins + 3;
-  static constexpr int kMagFloats = TF * kMagPitch;
-  static constexpr int kTileF2 = (NFFT == 1024 || kSplit2048) ? kTile512 : kTile1024;
+  static constexpr int kTileF2 = kTile512 ? (kMagsInTiles ? 546 : ::dmel::kTile512) : kTile1024;  // 546 float2 = 1092 floats = 4 (mod 32)
+  static constexpr int kMagPitch = kMagsInTiles ? 2 * kTileF2 : kBins + 3;
+  static constexpr int kMagFloats = kMagsInTiles ? 0 : TF * kMagPitch;
+  static_assert(kMagPitch % 4 == 0 && kMagPitch % 32 == 4, "conflict-free LDS.128 across eight frames");
+  static_assert(!kMagsInTiles || kMagPitch >= kBins + 3, "a magnitude row fits the transpose tile");
   static constexpr int kFoldN = NFFT / 4 + 1;
   // byte offsets inside dynamic shared memory (all 16-byte aligned)
   static __host__ __device__ constexpr size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
   static __host__ __device__ size_t tiles_off() { return 0; }
-  static __host__ __device__ size_t mags_off() { return size_t(kWarps) * kTileF2 * sizeof(float2); }
-  static __host__ __device__ size_t wave_off() { return align16(mags_off() + size_t(kMagFloats) * 4); }
+  static __host__ __device__ size_t mags_off() { return kMagsInTiles ? 0 : size_t(kWarps) * kTileF2 * sizeof(float2); }
+  static __host__ __device__ size_t wave_off() { return align16(size_t(kWarps) * kTileF2 * sizeof(float2) + size_t(kMagFloats) * 4); }
   static __host__ __device__ size_t window_off(int wave_len) { return align16(wave_off() + kWaveBufs * size_t(wave_len) * 4); }
   static __host__ __device__ size_t fold_off(int wave_len) {
     return align16(window_off(wave_len) + (kWindowInSmem ? size_t(NFFT) * 4 : 0));
   }
-  static __host__ __device__ size_t chan_off(int wave_len) {
+  static __host__ __device__ size_t weights_off(int wave_len) {
     return align16(fold_off(wave_len) + ((NFFT == 2048 && !kSplit2048) ? size_t(kFoldN) * 8 : 0));
   }
-  // n_chan = channel count padded to the group size
-  static __host__ __device__ size_t weights_off(int wave_len, int n_chan) {
-    return align16(chan_off(wave_len) + size_t(n_chan) * 8);
-  }
-  static __host__ __device__ size_t perchan_off(int wave_len, int n_chan, int nnz) {
-    return align16(weights_off(wave_len, n_chan) + size_t(nnz) * 4);
-  }
+  // n_chan = channel count padded to the group size.  The records follow the weights, so the mel loop's
+  // one-step read-ahead past the last span stays inside the allocation.
+  static __host__ __device__ size_t rec_off(int wave_len, int nnz) { return align16(weights_off(wave_len) + size_t(nnz) * 4); }
   static __host__ __device__ size_t bar_off(int wave_len, int n_chan, int nnz) {
-    return align16(perchan_off(wave_len, n_chan, nnz) + size_t(n_chan) * 12);  // {lo, scale, step} or {min, max}
+    return align16(rec_off(wave_len, nnz) + size_t(n_chan) * sizeof(ChanRec));
   }
   static __host__ __device__ size_t total(int wave_len, int n_chan, int nnz) {
-    return bar_off(wave_len, n_chan, nnz) + 32;  // two mbarriers + the next-tile slot
+    return bar_off(wave_len, n_chan, nnz) + 64;  // two mbarriers (16 B), the next tile's description (32 B), spare
   }
 };
 
@@ -200,12 +250,12 @@ struct TileInfo {
   // staging: wave[bulk_lo, bulk_lo + bulk_n) comes from one bulk async copy (the samples that exist and
   // need no reflection), the rest - nothing for interior tiles - from plain reflect-indexed loads
   int bulk_lo, bulk_n;
-  bool manual;      // some of the tile is staged by plain loads (row ends, unaligned rows)
+  int manual;       // some of the tile is staged by plain loads (row ends, unaligned rows)
   long long src0;   // flat waveform offset of wave[0]'s sample (valid inside the bulk range)
 };
 
 template <int NFFT, int TF, int MODE, int OCC>
-__global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_constant__ FusedParams p) {
   static_assert(OCC == 1 || (OCC == 2 && (NFFT == 1024 || TF == 8)) || (OCC == 3 && NFFT == 1024 && TF == 8),
                 "occupancy variants");
   static_assert(NFFT == 1024 || NFFT == 2048, "register FFT cores: 512 and 1024 complex points");
@@ -221,14 +271,11 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   constexpr bool kDequant = (MODE & kOutDequant) != 0;
   static_assert(!kDequant || kCodes, "kOutDequant qualifies the code output");
   static_assert(!kPcm || kLean, "int16 input is built for the register-lean variants");
+  static_assert(!(kCodes && kStats), "codes and statistics share the float half of the channel records");
+  static_assert(!kBf16 || kLogmel, "kOutBf16 qualifies the log-mel output");
   using wave_t = std::conditional_t<kPcm, short, float>;
   constexpr int kAlign = 16 / (int)sizeof(wave_t);  // samples per 16 bytes: granularity of the bulk copies
   const wave_t* wav = reinterpret_cast<const wave_t*>(p.wav);
-  static_assert(!kBf16 || kLogmel, "kOutBf16 qualifies the log-mel output");
-  auto store_logmel = [&](size_t o, float v) {
-    if constexpr (kBf16) reinterpret_cast<__nv_bfloat16*>(p.logmel)[o] = __float2bfloat16_rn(v);
-    else p.logmel[o] = v;
-  };
 
   extern __shared__ __align__(16) unsigned char smem[];
   float2* tiles = reinterpret_cast<float2*>(smem);
@@ -236,17 +283,12 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   wave_t* wave0 = reinterpret_cast<wave_t*>(smem + p.off_wave);
   float* s_window = reinterpret_cast<float*>(smem + p.off_window);
   float2* s_fold = reinterpret_cast<float2*>(smem + p.off_fold);
-  int2* s_chan = reinterpret_cast<int2*>(smem + p.off_chan);
   float* s_weights = reinterpret_cast<float*>(smem + p.off_weights);
-  // two per-channel arrays: quantiser {lo, scale} when writing codes, running {min, max} when
-  // calibrating (no launch does both)
-  static_assert(!(kCodes && kStats), "codes and statistics share their per-channel scratch");
-  float* s_lo = reinterpret_cast<float*>(smem + p.off_perchan);
-  float* s_scale = s_lo + p.n_chan_pad;
-  float* s_step = s_scale + p.n_chan_pad;
-  float* s_min = s_lo;
-  float* s_max = s_scale;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bars);
+  ChanRec* s_rec = reinterpret_cast<ChanRec*>(smem + p.off_rec);
+  // 32-bit shared addresses of the regions the mel phase and the bookkeeping touch
+  const uint32_t sa_base = smem_u32(smem);
+  const uint32_t sa_bar = sa_base + p.off_bars;   // bars[0], bars[1] at +0, +8
+  const uint32_t sa_slot = sa_bar + 16;           // {next tile, row, t0, n_valid}, {frame_limit, bulk_lo, bulk_n, manual}
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -255,13 +297,13 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   grid_launch_dependents();
 
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    mbar_init(sa_bar, 1);
+    mbar_init(sa_bar + 8, 1);
     fence_mbar_init();
   }
 
   // per-lane constants kept in registers for the whole kernel
-  constexpr int kPts = (NFFT == 1024 || kSplit) ? 16 : 32;  // complex points per lane
+  constexpr int kPts = LY::kTile512 ? 16 : 32;  // complex points per lane
   constexpr int kTwRegs = kLean ? 1 : kPts;
   float2 tw[kTwRegs];                           // inter-pass twiddles W_{NFFT/2}^{lane*k1}
   if constexpr (!kLean) {
@@ -292,19 +334,20 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   }
   const float2* my_win = reinterpret_cast<const float2*>(s_window) + lane;  // lean / 2048: taps re-read per frame
 
-  const int padded_len = p.n_samples + 2 * p.pad_inner + 2 * p.pad_outer;
   const bool hop_even = (p.hop & 1) == 0;
-  const bool row_vec_ok = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0) && ((p.row_stride & (kAlign - 1)) == 0);
   unsigned long long edge_hits = 0;
   uint32_t phase_bits = 0;  // bit b: parity to wait for on bars[b]
 
+  // Where tile `tile` sits and how its samples reach shared memory.  Two multiply-high divisions and a page of
+  // integer logic: evaluated by one thread per tile.
   auto describe = [&](int tile) {
     TileInfo ti;
-    ti.row = tile / p.tiles_per_row;
+    ti.row = (int)p.by_tiles_per_row.div((unsigned)tile);
     ti.t0 = (tile - ti.row * p.tiles_per_row) * TF;
     ti.n_valid = p.n_frames;  // in frames of this launch's window
     if (p.lengths) {
-      const int nv = p.lengths[ti.row] / p.hop - p.t_begin;
+      const int len = p.lengths[ti.row];
+      const int nv = (len <= 0 ? 0 : (int)p.by_hop.div((unsigned)len)) - p.t_begin;
       ti.n_valid = nv < 0 ? 0 : (nv < p.n_frames ? nv : p.n_frames);
     }
     // log-mel output covers every frame of the row (unless masked); codes / statistics only the valid ones
@@ -317,33 +360,35 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
     int lo = s0 < 0 ? ((-s0 + kA) & ~kA) : 0;                                 // first wave index with a real sample
     if (b0 + lo < 0) lo = (-b0 + kA) & ~kA;                                   // ... that is resident in the buffer
     int hi = p.n_samples - s0 < p.wave_len ? ((p.n_samples - s0) & ~kA) : p.wave_len;  // one past the last
+    const bool row_vec_ok = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0) && ((p.row_stride & (kAlign - 1)) == 0);
     const bool can_bulk = row_vec_ok && p.pad_outer == 0 && (b0 & kA) == 0 && hi > lo;
     ti.bulk_lo = can_bulk ? lo : 0;
     ti.bulk_n = can_bulk ? hi - lo : 0;
-    ti.manual = !can_bulk || lo > 0 || hi < p.wave_len;
+    ti.manual = (!can_bulk || lo > 0 || hi < p.wave_len) ? 1 : 0;
     return ti;
   };
-  // Start filling wave buffer b with the samples of a tile.
-  auto stage = [&](const TileInfo& ti, int b) {
-    if (ti.frame_limit == 0 || (p.debug_skip & 4)) return;
+  // thread 0: start the bulk async copy of a tile into wave buffer b
+  auto stage_bulk = [&](const TileInfo& ti, int b) {
+    if (ti.frame_limit == 0 || ti.bulk_n == 0 || DMEL_SKIP(p, 4)) return;
+    const uint32_t dst = sa_base + p.off_wave + (uint32_t)(b * p.wave_len + ti.bulk_lo) * (uint32_t)sizeof(wave_t);
+    fence_proxy_async();  // earlier generic-proxy reads of this buffer are ordered before the async write
+    mbar_expect_tx(sa_bar + 8 * b, ti.bulk_n * (int)sizeof(wave_t));
+    bulk_copy_g2s(dst, wav + ti.src0 + ti.bulk_lo, ti.bulk_n * (int)sizeof(wave_t), sa_bar + 8 * b);
+  };
+  // all threads: the part of a tile no bulk copy can bring (reflected row ends, unaligned rows)
+  auto stage_manual = [&](int row, int t0, int bulk_lo, int bulk_n, int b) {
+    if (DMEL_SKIP(p, 4)) return;
     wave_t* wave = wave0 + b * p.wave_len;
-    if (ti.bulk_n && tid == 0) {
-      fence_proxy_async();  // earlier generic-proxy reads of this buffer are ordered before the async write
-      mbar_expect_tx(&bars[b], ti.bulk_n * (int)sizeof(wave_t));
-      bulk_copy_g2s(wave + ti.bulk_lo, wav + ti.src0 + ti.bulk_lo, ti.bulk_n * (int)sizeof(wave_t), &bars[b]);
-    }
-    if (ti.manual) {
-      const wave_t* src = wav + (long long)ti.row * p.row_stride - p.src_base;
-      const int j0 = (p.t_begin + ti.t0) * p.hop;  // first position in the padded row
-      const int skip_lo = ti.bulk_lo, skip_hi = ti.bulk_lo + ti.bulk_n;
-      const int n_manual = p.wave_len - ti.bulk_n;
-      for (int q = tid; q < n_manual; q += kThreads) {
-        const int i = q < skip_lo ? q : q + (skip_hi - skip_lo);  // wave index outside the bulk range
-        const int j = j0 + i;
-        wave_t x = 0;
-        if (j < padded_len) x = __ldg(src + reflect_src(j, p.n_samples, p.pad_inner, p.pad_outer));
-        wave[i] = x;
-      }
+    const int padded_len = p.n_samples + 2 * p.pad_inner + 2 * p.pad_outer;
+    const wave_t* src = wav + (long long)row * p.row_stride - p.src_base;
+    const int j0 = (p.t_begin + t0) * p.hop;  // first position in the padded row
+    const int n_manual = p.wave_len - bulk_n;
+    for (int q = tid; q < n_manual; q += kThreads) {
+      const int i = q < bulk_lo ? q : q + bulk_n;  // wave index outside the bulk range
+      const int j = j0 + i;
+      wave_t x = 0;
+      if (j < padded_len) x = __ldg(src + reflect_src(j, p.n_samples, p.pad_inner, p.pad_outer));
+      wave[i] = x;
     }
   };
 
@@ -351,14 +396,18 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   // Everything up to grid_dependency_wait() reads plan-owned memory only (written at plan creation), so under
   // programmatic dependent launch it overlaps the tail of the previous kernel in the stream.
   for (int i = tid; i < p.n_chan_pad; i += kThreads) {
-    s_chan[i] = p.chan[i];
+    *reinterpret_cast<int4*>(&s_rec[i]) = p.chan[i];
     if constexpr (!kCodes) {
-      s_min[i] = __int_as_float(0x7f800000);
-      s_max[i] = __int_as_float(0xff800000);
+      s_rec[i].a = __int_as_float(0x7f800000);
+      s_rec[i].b = __int_as_float(0xff800000);
     }
   }
   for (int i = tid; i < p.nnz; i += kThreads) s_weights[i] = p.weights[i];
-  for (int i = tid; i < LY::kMagFloats; i += kThreads) mags[i] = 0.f;  // the 3 pad columns of each row stay zero
+  if constexpr (!LY::kMagsInTiles) {
+    for (int i = tid; i < LY::kMagFloats; i += kThreads) mags[i] = 0.f;  // the 3 pad columns of each row stay zero
+  } else {
+    for (int i = tid; i < kWarps * LY::kTileF2; i += kThreads) tiles[i] = make_float2(0.f, 0.f);  // rows of frames never computed read as finite
+  }
   if constexpr (LY::kWindowInSmem) {
     for (int i = tid; i < NFFT; i += kThreads) s_window[i] = p.window[i];
   }
@@ -367,50 +416,65 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   }
   grid_dependency_wait();  // from here on: the caller's tensors (waveform, lengths, statistics, outputs, tile counter)
   int tile = blockIdx.x;
-  TileInfo cur = describe(tile < p.n_tiles ? tile : 0);
-  if (tile < p.n_tiles) stage(cur, 0);  // the first tile leaves HBM while the statistics below are fetched
+  TileInfo first = describe(tile < p.n_tiles ? tile : 0);
+  if (tile < p.n_tiles) {
+    if (tid == 0) stage_bulk(first, 0);  // the first tile leaves HBM while the statistics below are fetched
+    if (first.manual && first.frame_limit) stage_manual(first.row, first.t0, first.bulk_lo, first.bulk_n, 0);
+  }
   if constexpr (kCodes) {
     for (int i = tid; i < p.n_chan_pad; i += kThreads) {
       const bool real = i < p.n_mels;
-      s_lo[i] = real ? p.q_lo[i] : 0.f;
-      s_scale[i] = real ? p.q_scale[i] : 0.f;
-      if constexpr (kDequant) s_step[i] = real ? p.q_step[i] : 0.f;
+      s_rec[i].a = real ? p.q_lo[i] : 0.f;
+      s_rec[i].b = real ? p.q_scale[i] : 0.f;
+      if constexpr (kDequant) s_rec[i].c = real ? p.q_step[i] : 0.f;
     }
   }
   __syncthreads();  // constants + barrier init visible
   // Tiles after the first are handed out by a global counter (lean variants), so the CTAs of the
   // grid finish within one tile of each other instead of one or two tiles apart.
   constexpr bool kDynamic = LY::kWaveBufs == 1;
-  int* s_next = reinterpret_cast<int*>(bars + 2);
   const bool dynamic = kDynamic && p.sched != nullptr;
+
+  // CTA-uniform description of the current tile (every thread holds a copy)
+  int cur_row = first.row, cur_t0 = first.t0, cur_valid = first.n_valid, cur_limit = first.frame_limit;
+  int cur_bulk = first.bulk_n;  // (plain-load staging is ordered by the barrier that closes the previous tile)
 
   for (int it = 0; tile < p.n_tiles; ++it) {
     const int b = LY::kWaveBufs == 2 ? (it & 1) : 0;
     const wave_t* wave = wave0 + b * p.wave_len;
-    const bool dead = cur.frame_limit == 0;
+    const bool dead = cur_limit == 0;
 
-    // ---- 1. this tile's samples are in wave[b]; start fetching the next tile
-    if (!dead && !(p.debug_skip & 4)) {
-      if (cur.bulk_n) {
-        mbar_wait(&bars[b], (phase_bits >> b) & 1u);
+    // ---- 1. this tile's samples are in wave[b]
+    if (!dead && !DMEL_SKIP(p, 4)) {
+      if (cur_bulk) {
+        mbar_wait(sa_bar + 8 * b, (phase_bits >> b) & 1u);
         phase_bits ^= 1u << b;
       }
-      if (cur.manual) __syncthreads();  // plain stores of all threads
     }
-    int next_tile = tile + (int)gridDim.x;
+    // thread 0 finds out which tile comes next and describes it; with two wave buffers its copy starts now
     int fetched = 0;
-    if (dynamic && tid == 0) fetched = atomicAdd(p.sched, 1);  // consumed just before the barrier below
-    bool has_next = next_tile < p.n_tiles;
-    TileInfo nxt = cur;
-    if constexpr (!kDynamic) {
-      nxt = describe(has_next ? next_tile : tile);
-      if constexpr (LY::kWaveBufs == 2) {
-        if (has_next) stage(nxt, b ^ 1);  // double buffered: the next tile loads while this one computes
+    TileInfo nd;
+    nd.bulk_n = 0;
+    nd.frame_limit = 0;
+    if (tid == 0) {
+      if constexpr (kDynamic) {
+        if (dynamic) fetched = atomicAdd(p.sched, 1);  // consumed after the FFT: its latency is never waited for
+      } else {
+        const int next_tile = tile + (int)gridDim.x;
+        int4 s0 = make_int4(next_tile, 0, 0, 0), s1 = make_int4(0, 0, 0, 0);
+        if (next_tile < p.n_tiles) {
+          nd = describe(next_tile);
+          stage_bulk(nd, b ^ 1);  // double buffered: the next tile loads while this one computes
+          s0 = make_int4(next_tile, nd.row, nd.t0, nd.n_valid);
+          s1 = make_int4(nd.frame_limit, nd.bulk_lo, nd.bulk_n, nd.manual);
+        }
+        sts_i4(sa_slot, s0);
+        sts_i4(sa_slot + 16, s1);
       }
     }
 
     // ---- 2. FFT -> magnitudes ------------------------------------------------
-    const int fft_frames = (p.debug_skip & 1) ? 0 : cur.frame_limit;
+    const int fft_frames = DMEL_SKIP(p, 1) ? 0 : cur_limit;
     if constexpr (NFFT == 1024) {
       const int h = lane >> 4;
       const int partner = mirror_lane512(lane);
@@ -437,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
             else v[n1] = f2_mul(xf, win[n1]);
           }
         }
-        __syncwarp();  // previous frame's pass-2 reads of my_tile are done
+        __syncwarp();  // previous readers of my_tile (pass 2 of the previous frame, or the previous tile's mel phase) are done
         if constexpr (kLean) fft512_pass1_pow(v, w1, w2, w4, w8, my_tile, lane);
         else fft512_pass1(v, tw, my_tile, lane);
         __syncwarp();
@@ -452,7 +516,13 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           recv[j] = make_float2(__shfl_sync(0xffffffffu, send[j].x, partner), __shfl_sync(0xffffffffu, send[j].y, partner));
-        unfold_store512(zlo, zhi, recv, fold_base, mags + fr * kPitch, lane);
+        // with kMagsInTiles the row is the warp's own tile: every lane's pass-2 loads have returned (the
+        // shuffles above needed them), so it is free to be overwritten
+        float* mrow = LY::kMagsInTiles ? reinterpret_cast<float*>(my_tile) : mags + fr * kPitch;
+        unfold_store512(zlo, zhi, recv, fold_base, mrow, lane);
+        if constexpr (LY::kMagsInTiles) {
+          if (lane < 3) mrow[513 + lane] = 0.f;  // the pad columns a 16-byte aligned span may touch (zero weight)
+        }
       }
     } else if constexpr (kSplit) {
       const int h = lane >> 4;
@@ -503,7 +573,11 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
         HalfSpectrum e, o;
         half(v, e);
         half(odd, o);
-        combine2048_store(e, o, base2048, mags + fr * kPitch, lane);
+        float* mrow = LY::kMagsInTiles ? reinterpret_cast<float*>(my_tile) : mags + fr * kPitch;
+        combine2048_store(e, o, base2048, mrow, lane);
+        if constexpr (LY::kMagsInTiles) {
+          if (lane < 3) mrow[1025 + lane] = 0.f;
+        }
       }
     } else {
 #pragma unroll 1
@@ -541,37 +615,47 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
       }
     }
     if constexpr (kDynamic) {
-      if (dynamic && tid == 0) *s_next = (int)gridDim.x + fetched;
+      if (tid == 0) {  // describe the next tile (one thread: the others only read the result)
+        const int next_tile = dynamic ? (int)gridDim.x + fetched : tile + (int)gridDim.x;
+        int4 s0 = make_int4(next_tile, 0, 0, 0), s1 = make_int4(0, 0, 0, 0);
+        if (next_tile < p.n_tiles) {
+          nd = describe(next_tile);
+          s0 = make_int4(next_tile, nd.row, nd.t0, nd.n_valid);
+          s1 = make_int4(nd.frame_limit, nd.bulk_lo, nd.bulk_n, nd.manual);
+        }
+        sts_i4(sa_slot, s0);
+        sts_i4(sa_slot + 16, s1);
+      }
     }
-    __syncthreads();
-    if constexpr (kDynamic) {
-      if (dynamic) next_tile = *s_next;
-      has_next = next_tile < p.n_tiles;
-      nxt = describe(has_next ? next_tile : tile);
-    }
+    __syncthreads();  // magnitudes complete, wave[b] free, the slot describes the next tile
     if constexpr (LY::kWaveBufs == 1) {
-      if (has_next) stage(nxt, 0);  // single buffer: it is free now, the copy flies under the mel phase
+      if (tid == 0) stage_bulk(nd, 0);  // single buffer: it is free now, the copy flies under the mel phase
     }
+    const int4 nx0 = lds_i4(sa_slot), nx1 = lds_i4(sa_slot + 16);
+    const int next_tile = nx0.x;
+    if (next_tile < p.n_tiles && nx1.w && nx1.x)
+      stage_manual(nx0.y, nx0.z, nx1.y, nx1.z, LY::kWaveBufs == 2 ? (b ^ 1) : 0);
 
     // ---- 3. mel filterbank, log, quantise --------------------------------
     // One lane per frame, 32/TF adjacent channels side by side in a warp.  The host pads the spans
     // of such a channel group to one common length, so the bin loop is warp-uniform.
-    {
+    if (!DMEL_SKIP(p, 2)) {
       constexpr int kGroups = 32 / TF;
       constexpr int kStep = kWarps * kGroups;  // channels between two trips of a lane
       const int fr = lane % TF;
       const int sub = lane / TF;
-      const int t = cur.t0 + fr;
-      const bool in_row = t < p.n_frames;
-      const bool valid = t < cur.n_valid;
-      const float* mrow = mags + fr * kPitch;
+      const int t = cur_t0 + fr;
       const int m0 = warp * kGroups + sub;
       const size_t ostep = (size_t)kStep * p.n_frames;
-      size_t o = ((size_t)cur.row * p.n_mels + m0) * p.n_frames + t;
-      if (p.debug_skip & 2) {
-      } else if (dead) {
+      size_t o = ((size_t)cur_row * p.n_mels + m0) * p.n_frames + t;
+      auto store_logmel = [&](size_t at, float v) {
+        if constexpr (kBf16) reinterpret_cast<__nv_bfloat16*>(p.logmel)[at] = __float2bfloat16_rn(v);
+        else p.logmel[at] = v;
+      };
+      if (dead) {
         // nothing of this tile is valid audio: codes are the pad value, masked log-mel is zero
         if constexpr (kCodes || kLogmel) {
+          const bool in_row = t < p.n_frames;
 #pragma unroll 1
           for (int m = m0; m < p.n_mels; m += kStep, o += ostep)
             if (in_row) {
@@ -581,71 +665,120 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
             }
         }
       } else {
-        const int2* cp = s_chan + m0;
-        const float* lop = s_lo + m0;
-        const float* scp = s_scale + m0;
-#pragma unroll 1
-        for (int mb = warp * kGroups; mb < p.n_chan_pad; mb += kStep, cp += kStep, lop += kStep, scp += kStep, o += ostep) {
-          const int m = mb + sub;
-          const bool live = m < p.n_mels;
-          const int2 c = *cp;
-          const float4* w4 = reinterpret_cast<const float4*>(s_weights + c.y);
-          const float4* x4 = reinterpret_cast<const float4*>(mrow + (c.x & 0xffff));
-          const float4* x4_end = x4 + (c.x >> 18);  // span length / 4: >= 1, identical across the warp
-          float acc = 0.f;
+        const uint32_t xrow = sa_base + p.off_mags + (uint32_t)fr * (kPitch * 4);
+        const uint32_t wbase = sa_base + p.off_weights;
+        uint32_t rec = sa_base + p.off_rec + (uint32_t)m0 * (uint32_t)sizeof(ChanRec);
+        // A tile is `full` when all TF frames are valid frames of the row and no phantom channel pads a group:
+        // the common case, and the one whose epilogue carries no predicates.
+        const bool full = (cur_t0 + TF <= cur_valid) && (p.n_chan_pad == p.n_mels);
+        // banded dot product of this lane's frame with the channel the record describes
+        auto channel_value = [&](const int4& c) {
+          uint32_t wa = wbase + c.y, xa = xrow + c.x;
+          const uint32_t xe = xa + c.z;
+          float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll 1
           do {
-            const float4 w = *w4++;
-            const float4 x = *x4++;
-            acc = fmaf(w.x, x.x, acc);
-            acc = fmaf(w.y, x.y, acc);
-            acc = fmaf(w.z, x.z, acc);
-            acc = fmaf(w.w, x.w, acc);
-          } while (x4 != x4_end);
-          const float value = fast_log(fmaxf(acc, kLogClip));
-          if constexpr (kLogmel) {
-            const float out = (p.mask_invalid && !valid) ? 0.f : value;
-            if (live && in_row) store_logmel(o, out);
-            if (p.row_sum) {  // per (row, channel) sum over time: the caller's mels.mean(-1) without another pass
-              float part = (live && in_row) ? out : 0.f;
+            const float4 w = lds_f4(wa);
+            const float4 x = lds_f4(xa);
+            wa += 16;
+            xa += 16;
+            acc0 = fmaf(w.x, x.x, acc0);
+            acc1 = fmaf(w.y, x.y, acc1);
+            acc0 = fmaf(w.z, x.z, acc0);
+            acc1 = fmaf(w.w, x.w, acc1);
+          } while (xa != xe);
+          return fast_log(fmaxf(acc0 + acc1, kLogClip));
+        };
+        if (full) {
+#pragma unroll 1
+          for (int mb = warp * kGroups; mb < p.n_chan_pad; mb += kStep, rec += kStep * (int)sizeof(ChanRec), o += ostep) {
+            const int4 c = lds_i4(rec);
+            const float4 q = lds_f4(rec + 16);
+            const float value = channel_value(c);
+            if constexpr (kLogmel) {
+              store_logmel(o, value);
+              if (p.row_sum) {  // per (row, channel) sum over time: the caller's mels.mean(-1) without another pass
+                float part = value;
 #pragma unroll
-              for (int d = TF / 2; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-              if (fr == 0 && live) atomicAdd(p.row_sum + (size_t)cur.row * p.n_mels + m, part);
+                for (int d = TF / 2; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                if (fr == 0) atomicAdd(p.row_sum + (size_t)cur_row * p.n_mels + mb + sub, part);
+              }
+            }
+            if constexpr (kCodes) {
+              const float pos = __fmul_rn(__fsub_rn(value, q.x), q.y);
+              const float qf = fminf(fmaxf(floorf(pos), 0.f), p.kmax);
+              p.codes[o] = (unsigned char)qf;
+              if constexpr (kDequant)  // the table entry the stand-alone decoder would look up, same two roundings
+                p.dequant[o] = __fadd_rn(q.x, __fmul_rn(qf + 0.5f, q.z));
+              if constexpr (kEdge) {
+                const float e = fminf(fmaxf(rintf(pos), 1.f), p.kmax);
+                if (fabsf(pos - e) < p.edge_eps * q.y) ++edge_hits;
+              }
+            }
+            if constexpr (kStats) {
+              float lo = value, hi = value;
+#pragma unroll
+              for (int d = TF / 2; d >= 1; d >>= 1) {
+                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+              }
+              if (fr == 0) sts_f2(rec + 16, fminf(q.x, lo), fmaxf(q.y, hi));  // channel m always belongs to this lane of this warp: no race
             }
           }
-          if constexpr (kCodes) {
-            const float sc = *scp;
-            const float pos = __fmul_rn(__fsub_rn(value, *lop), sc);
-            const float q = fminf(fmaxf(floorf(pos), 0.f), p.kmax);
-            if (live && in_row) p.codes[o] = valid ? (unsigned char)q : (unsigned char)0;
-            if constexpr (kDequant) {  // the table entry the stand-alone decoder would look up, same two roundings
-              const float centre = __fadd_rn(*lop, __fmul_rn(q + 0.5f, s_step[m]));
-              if (live && in_row) p.dequant[o] = valid ? centre : 0.f;
-            }
-            if constexpr (kEdge) {
-              const float e = fminf(fmaxf(rintf(pos), 1.f), p.kmax);
-              if (live && valid && fabsf(pos - e) < p.edge_eps * sc) ++edge_hits;
-            }
-          }
-          if constexpr (kStats) {
-            float lo = (valid && live) ? value : __int_as_float(0x7f800000);
-            float hi = (valid && live) ? value : __int_as_float(0xff800000);
+        } else {
+          const bool in_row = t < p.n_frames;
+          const bool valid = t < cur_valid;
+#pragma unroll 1
+          for (int mb = warp * kGroups; mb < p.n_chan_pad; mb += kStep, rec += kStep * (int)sizeof(ChanRec), o += ostep) {
+            const int m = mb + sub;
+            const bool live = m < p.n_mels;
+            const int4 c = lds_i4(rec);
+            const float4 q = lds_f4(rec + 16);
+            const float value = channel_value(c);
+            if constexpr (kLogmel) {
+              const float out = (p.mask_invalid && !valid) ? 0.f : value;
+              if (live && in_row) store_logmel(o, out);
+              if (p.row_sum) {
+                float part = (live && in_row) ? out : 0.f;
 #pragma unroll
-            for (int d = TF / 2; d >= 1; d >>= 1) {
-              lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-              hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+                for (int d = TF / 2; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                if (fr == 0 && live) atomicAdd(p.row_sum + (size_t)cur_row * p.n_mels + m, part);
+              }
             }
-            if (fr == 0 && live) {  // channel m always belongs to this lane of this warp: no race
-              s_min[m] = fminf(s_min[m], lo);
-              s_max[m] = fmaxf(s_max[m], hi);
+            if constexpr (kCodes) {
+              const float pos = __fmul_rn(__fsub_rn(value, q.x), q.y);
+              const float qf = fminf(fmaxf(floorf(pos), 0.f), p.kmax);
+              if (live && in_row) p.codes[o] = valid ? (unsigned char)qf : (unsigned char)0;
+              if constexpr (kDequant) {
+                const float centre = __fadd_rn(q.x, __fmul_rn(qf + 0.5f, q.z));
+                if (live && in_row) p.dequant[o] = valid ? centre : 0.f;
+              }
+              if constexpr (kEdge) {
+                const float e = fminf(fmaxf(rintf(pos), 1.f), p.kmax);
+                if (live && valid && fabsf(pos - e) < p.edge_eps * q.y) ++edge_hits;
+              }
+            }
+            if constexpr (kStats) {
+              float lo = (valid && live) ? value : __int_as_float(0x7f800000);
+              float hi = (valid && live) ? value : __int_as_float(0xff800000);
+#pragma unroll
+              for (int d = TF / 2; d >= 1; d >>= 1) {
+                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+              }
+              if (fr == 0 && live) sts_f2(rec + 16, fminf(q.x, lo), fmaxf(q.y, hi));
             }
           }
         }
       }
     }
-    __syncthreads();  // mags and wave[b] are free again
-    cur = nxt;
+    __syncthreads();  // magnitudes and the slot are free again; manual stores of the next tile are visible
     tile = next_tile;
+    cur_row = nx0.y;
+    cur_t0 = nx0.z;
+    cur_valid = nx0.w;
+    cur_limit = nx1.x;
+    cur_bulk = nx1.z;
   }
   if constexpr (kDynamic) {
     // the last CTA to finish leaves both counters at zero for the next launch
@@ -661,7 +794,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const FusedPa
   // ---- flush per-CTA statistics -------------------------------------------
   if constexpr (kStats) {
     for (int m = tid; m < p.n_mels; m += kThreads) {
-      const float lo = s_min[m], hi = s_max[m];
+      const float lo = s_rec[m].a, hi = s_rec[m].b;
       if (lo <= hi) {
         atomic_min_float(p.run_min + m, lo);
         atomic_max_float(p.run_max + m, hi);
