@@ -65,7 +65,9 @@ struct dmel_plan {
   int ctas_per_sm = 1;
   int wave_len = 0;
   int nnz = 0;
-  int n_chan_pad = 0;  // n_mels rounded up to the channel-group size 32 / tile_frames
+  int n_chan_pad = 0;  // n_mels rounded up to the channel-group size 2 * 32 / tile_frames
+  int n_order = 0;     // entries of the group-order table
+  int* d_order = nullptr;
   size_t smem_bytes = 0;
   const dmel::VariantOps* variant = nullptr;  // the kernel variant chosen for this geometry
   float* d_window = nullptr;
@@ -100,9 +102,12 @@ const dmel::VariantOps* const kVariants[] = {
 
 constexpr unsigned kSchedSlots = 64;
 
-cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int grid, cudaStream_t st,
+cudaError_t launch_fused_any(const dmel_plan* plan, FusedParams& p, int grid, cudaStream_t st,
                              bool bf16_logmel = false, bool pcm16 = false) {
   using namespace dmel;
+  // bulk async copies move whole 16-byte units: the waveform base and the row stride must be multiples of 16 bytes
+  const long long per16 = pcm16 ? 8 : 4;
+  p.bulk_ok = (reinterpret_cast<uintptr_t>(p.wav) & 15) == 0 && p.row_stride % per16 == 0 && p.pad_outer == 0;
   int mode = 0;
   if (p.codes) mode |= kOutCodes;
   if (p.logmel) mode |= kOutLogmel;
@@ -116,14 +121,18 @@ cudaError_t launch_fused_any(const dmel_plan* plan, const FusedParams& p, int gr
 
 // Banded form of the (n_mels, n_freq) filterbank the kernel reads: per channel the contiguous
 // non-zero span, starting on a multiple of 4 bins (the kernel fetches magnitudes with 16-byte
-// loads).  `group` adjacent channels are evaluated side by side in one warp, so their spans are
-// zero-padded to one common length (a multiple of 4, at least 4) and phantom channels complete
-// the last group; the bin loop is then uniform across the warp.
-void band_filterbank(const float* basis, int n_mels, int n_freq, int group, std::vector<int4>* chan,
-                     std::vector<float>* weights) {
+// loads).  A lane evaluates the channel PAIR (m, m + lanes) in one loop and `lanes` such pairs sit
+// side by side in a warp (lanes = 32 / frames per tile), so the spans of a group of 2 * lanes adjacent
+// channels are zero-padded to one common length (a multiple of 4, at least 4), phantom channels complete
+// the last group, and the weights of a pair are interleaved in steps of four bins:
+//   [4 weights of m][4 weights of m + lanes][next 4 of m][next 4 of m + lanes] ...
+void band_filterbank(const float* basis, int n_mels, int n_freq, int lanes, std::vector<int4>* chan,
+                     std::vector<float>* weights, std::vector<int>* group_steps) {
+  const int group = 2 * lanes;
   const int n_pad = (n_mels + group - 1) / group * group;
   chan->assign(n_pad, make_int4(0, 0, 16, 0));
   weights->clear();
+  group_steps->clear();
   std::vector<int> first(n_pad, 0), last(n_pad, -1);
   for (int m = 0; m < n_mels; ++m) {
     const float* row = basis + (size_t)m * n_freq;
@@ -136,20 +145,58 @@ void band_filterbank(const float* basis, int n_mels, int n_freq, int group, std:
     first[m] = f0 < 0 ? 0 : (f0 & ~3);
     last[m] = f1;
   }
+  auto weight = [&](int m, int f) { return (m < n_mels && f >= 0 && f <= last[m]) ? basis[(size_t)m * n_freq + f] : 0.f; };
   for (int g = 0; g < n_pad; g += group) {
     int count = 4;
     for (int m = g; m < g + group; ++m) count = std::max(count, (last[m] - first[m] + 1 + 3) / 4 * 4);
-    const int pitch = n_freq + 3;  // FusedLayout::kMagPitch, a multiple of 4
-    for (int m = g; m < g + group; ++m) {
-      first[m] = std::min(first[m], pitch - count);  // keep the padded span inside the frame's row
+    group_steps->push_back(count / 4);
+    const int pitch = n_freq + 3;  // bins of a magnitude row the kernel keeps finite (a multiple of 4)
+    for (int m = g; m < g + group; ++m) first[m] = std::min(first[m], pitch - count);  // keep the padded span inside the row
+    for (int s = 0; s < lanes; ++s) {
+      const int ma = g + s, mb = g + lanes + s;
+      const int base = (int)weights->size();
       // the integer half of dmel::ChanRec, in bytes: {first bin, first weight, span length, -}
-      (*chan)[m] = make_int4(first[m] * 4, (int)weights->size() * 4, count * 4, 0);
-      for (int i = 0; i < count; ++i) {
-        const int f = first[m] + i;
-        weights->push_back((m < n_mels && f >= 0 && f <= last[m]) ? basis[(size_t)m * n_freq + f] : 0.f);
+      (*chan)[ma] = make_int4(first[ma] * 4, base * 4, count * 4, 0);
+      (*chan)[mb] = make_int4(first[mb] * 4, (base + 4) * 4, count * 4, 0);
+      for (int i = 0; i < count; i += 4) {
+        for (int j = 0; j < 4; ++j) weights->push_back(weight(ma, first[ma] + i + j));
+        for (int j = 0; j < 4; ++j) weights->push_back(weight(mb, first[mb] + i + j));
       }
     }
   }
+}
+
+// Deals the channel groups to the 8 warps of a CTA so that every warp runs about the same number of bin-loop
+// steps in the mel phase (longest group first, always to the least loaded warp).  Warp 0 starts with a handicap:
+// one of its threads describes the next tile and starts its copy while the others are already in the mel phase.
+// order[r * 8 + w] = group of warp w in its r-th trip, -1 = none.
+std::vector<int> deal_groups(const std::vector<int>& group_steps) {
+  constexpr int kW = dmel::kWarps;
+  const int kEpilogue = 3, kHandicap = 5;  // in steps: fixed cost per group (records, log, quantise, stores); warp 0's extra work
+  std::vector<int> idx(group_steps.size());
+  for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+  if (const char* env = std::getenv("DMEL_GROUP_ORDER"); env && std::strcmp(env, "identity") == 0) {
+    // measurements only: groups in channel order, round robin over the warps
+    std::vector<int> order((idx.size() + kW - 1) / kW * kW, -1);
+    for (size_t i = 0; i < idx.size(); ++i) order[i] = (int)i;
+    return order;
+  }
+  std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return group_steps[a] > group_steps[b]; });
+  std::vector<std::vector<int>> mine(kW);
+  int load[kW] = {kHandicap};
+  for (int g : idx) {
+    int w = 0;
+    for (int k = 1; k < kW; ++k)
+      if (load[k] < load[w]) w = k;
+    mine[w].push_back(g);
+    load[w] += group_steps[g] + kEpilogue;
+  }
+  size_t rounds = 0;
+  for (const auto& m : mine) rounds = std::max(rounds, m.size());
+  std::vector<int> order(rounds * kW, -1);
+  for (int w = 0; w < kW; ++w)
+    for (size_t r = 0; r < mine[w].size(); ++r) order[r * kW + w] = mine[w][r];
+  return order;
 }
 
 long long num_frames(const dmel_plan* plan, long long n_samples) {
@@ -212,6 +259,8 @@ int prepare_window(dmel_plan* plan, const float* wav, long long n_rows, long lon
   p->stage_tw = plan->d_stage_tw;
   p->fold_tw = plan->d_fold_tw;
   p->chan = plan->d_chan;
+  p->group_order = plan->d_order;
+  p->n_order = plan->n_order;
   p->weights = plan->d_weights;
   p->n_bins = 1;
   p->kmax = 0.f;
@@ -305,11 +354,13 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
   const int occ_pin = occ_env ? std::atoi(occ_env) : 0;
   std::vector<int4> chan;
   std::vector<float> weights;
+  std::vector<int> group_steps, order;
   for (const dmel::VariantOps* v : kVariants) {
     if (v->n_fft != n_fft || (occ_pin && v->occ != occ_pin)) continue;
-    band_filterbank(mel_basis_host, n_mels, n_fft / 2 + 1, 32 / v->tf, &chan, &weights);
+    band_filterbank(mel_basis_host, n_mels, n_fft / 2 + 1, 32 / v->tf, &chan, &weights, &group_steps);
+    order = deal_groups(group_steps);
     const int wave_len = ((v->tf - 1) * hop_length + n_fft + 7) / 8 * 8;  // whole 16-byte units of float and of int16
-    const size_t need = v->smem_need(wave_len, (int)chan.size(), (int)weights.size());
+    const size_t need = v->smem_need(wave_len, (int)chan.size(), (int)weights.size(), (int)order.size());
     const size_t limit = std::min<size_t>((size_t)max_sm_smem / v->occ - 1024, (size_t)plan->max_smem);  // 1 KB/CTA reserved
     if (need <= limit) {
       plan->variant = v;
@@ -319,6 +370,7 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
       plan->ctas_per_sm = v->occ;
       plan->nnz = (int)weights.size();
       plan->n_chan_pad = (int)chan.size();
+      plan->n_order = (int)order.size();
       break;
     }
   }
@@ -350,6 +402,7 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
   if (e == cudaSuccess) e = upload(&plan->d_fold_tw, fold_tw);
   if (e == cudaSuccess) e = upload(&plan->d_chan, chan);
   if (e == cudaSuccess) e = upload(&plan->d_weights, weights);
+  if (e == cudaSuccess) e = upload(&plan->d_order, order);
   if (e == cudaSuccess) e = upload(&plan->d_sched, std::vector<int>(2 * kSchedSlots, 0));
   if (e != cudaSuccess) {
     dmel_plan_destroy(plan);
@@ -368,6 +421,7 @@ void dmel_plan_destroy(dmel_plan* plan) {
   cudaFree(plan->d_fold_tw);
   cudaFree(plan->d_chan);
   cudaFree(plan->d_weights);
+  cudaFree(plan->d_order);
   cudaFree(plan->d_sched);
   for (int i = 0; i < 2; ++i) {
     cudaFree(plan->d_wav[i]);

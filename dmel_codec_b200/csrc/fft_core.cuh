@@ -55,14 +55,15 @@ DMEL_HD constexpr float sin32(int q) { return q <= 8 ? cos32_q(8 - q) : cos32_q(
 // sm_100 can execute add/mul/fma on an aligned register PAIR in one instruction (PTX
 // add/mul/fma.rn.f32x2, SASS FADD2/FMUL2/FFMA2) with free operand swizzles (swap halves, negate
 // one half, broadcast a scalar): a complex add is one instruction, a complex multiply two.
-// Build with -DDMEL_PACKED_F32X2 to use them.  Measured on B200 (profiles/history.md): warp
-// instructions per frame drop 1496 -> 1201, but a packed op holds the FMA pipe for two issue
-// cycles (benchmarks/fp_issue_rate.cu: 3.9 scalar vs 2.0 packed warp-instructions/cycle/SM), IPC
-// falls by the same factor and the kernel time is identical (117.5 vs 117.4 us).  The scalar
-// form stays the default; either way the host versions spell out the same operations in the
-// same order for tests/host_emul.cu.
-#if !defined(__CUDA_ARCH__)
-#undef DMEL_PACKED_F32X2
+// A packed op holds the FMA pipe for two cycles (benchmarks/fp_issue_rate.cu: same flops per cycle
+// as scalar) but takes ONE issue slot, and the slot it frees is usable by the other pipes
+// (benchmarks/f32x2_coissue.cu: 4 FFMA2 + 16 ALU instructions issue in 24 cycles, 8 FFMA + 16 ALU in
+// 34).  The fused kernel is bound by issue slots, so packed arithmetic is the default (-4.4 % time,
+// profiles/history.md); -DDMEL_SCALAR_F32 builds the scalar form.  Both forms round identically
+// (each half is an IEEE fma), and the host versions spell out the same operations in the same order
+// for tests/host_emul.cu.
+#if defined(__CUDA_ARCH__) && !defined(DMEL_SCALAR_F32)
+#define DMEL_PACKED_F32X2 1
 #endif
 #ifdef DMEL_PACKED_F32X2
 __device__ __forceinline__ unsigned long long f2_pack(float2 a) {

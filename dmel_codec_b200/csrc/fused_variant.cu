@@ -19,7 +19,7 @@ using LY = FusedLayout<NFFT, TF, OCC>;
 constexpr bool kLeanVariant = OCC == 3 || LY::kSplit2048;
 constexpr int kMaxDevices = 64;
 
-size_t smem_need(int wave_len, int n_chan, int nnz) { return LY::total(wave_len, n_chan, nnz); }
+size_t smem_need(int wave_len, int n_chan, int nnz, int n_order) { return LY::total(wave_len, n_chan, nnz, n_order); }
 
 void fill_offsets(FusedParams* p) {
   p->off_mags = (int)LY::mags_off();
@@ -28,7 +28,8 @@ void fill_offsets(FusedParams* p) {
   p->off_fold = (int)LY::fold_off(p->wave_len);
   p->off_weights = (int)LY::weights_off(p->wave_len);
   p->off_rec = (int)LY::rec_off(p->wave_len, p->nnz);
-  p->off_bars = (int)LY::bar_off(p->wave_len, p->n_chan_pad, p->nnz);
+  p->off_order = (int)LY::order_off(p->wave_len, p->n_chan_pad, p->nnz);
+  p->off_bars = (int)LY::bar_off(p->wave_len, p->n_chan_pad, p->nnz, p->n_order);
 }
 
 template <int MODE>

@@ -12,7 +12,7 @@ struct FusedParams;
 struct VariantOps {
   int n_fft, tf, occ;  // transform size, frames per tile, CTAs per SM the variant is built for
   bool lean;           // register-lean variant (the only ones with int16 PCM input)
-  size_t (*smem_need)(int wave_len, int n_chan, int nnz);
+  size_t (*smem_need)(int wave_len, int n_chan, int nnz, int n_order);
   void (*fill_offsets)(FusedParams* p);
   // mode = OR of the kOut* / kIn* bits of logmel_kernel.cuh; cudaErrorInvalidValue for a combination that is not built
   cudaError_t (*launch)(int mode, const FusedParams& p, int grid, size_t smem_bytes, cudaStream_t st);

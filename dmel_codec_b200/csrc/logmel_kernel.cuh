@@ -79,12 +79,15 @@ struct FusedParams {
   int n_chan_pad;           // n_mels rounded up to the channel-group size 32/TF
   int wave_len;             // staged samples per tile (multiple of 8)
   int nnz;                  // banded weights
+  int bulk_ok;              // waveform base and row stride are 16-byte aligned and center=False: tiles can be bulk-copied
+  int n_order;              // entries of group_order (a multiple of the warp count)
   FastDiv by_tiles_per_row; // tile -> row
   FastDiv by_hop;           // length -> valid frames
   const float* window;      // (n_fft)
   const float2* stage_tw;   // n_fft 1024: [16][32] W_512^{k1*n2}; n_fft 2048: [32][32] W_1024^{k1*n2}
   const float2* fold_tw;    // [n_fft/4 + 1]: W_{n_fft}^k
   const int4* chan;         // (n_chan_pad) {x_off, w_off, span, 0}: the integer half of ChanRec
+  const int* group_order;   // (n_order) channel group of warp w in its r-th trip at [r * warps + w], -1 = none: balances the mel phase
   const float* weights;
   const int* lengths;       // valid samples per row, or null
   float* logmel;            // (B, M, T)            [kOutLogmel]; __nv_bfloat16 with kOutBf16
@@ -99,7 +102,7 @@ struct FusedParams {
   float kmax;               // float(n_bins - 1)
   // byte offsets of the shared-memory regions (FusedLayout, filled in by the host so the kernel
   // does no layout arithmetic)
-  int off_mags, off_wave, off_window, off_fold, off_rec, off_weights, off_bars;
+  int off_mags, off_wave, off_window, off_fold, off_rec, off_weights, off_order, off_bars;
   int* sched;               // {next dynamic tile, finished CTAs}, both 0 between launches; null = static tile walk
   int debug_skip;           // diagnostics (env DMEL_DEBUG_SKIP, builds with -DDMEL_ABLATION only): 1 skip the FFT phase, 2 skip mel/epilogue, 4 skip staging
   float* run_min;           // (M) running min, updated in place [kOutStats]
@@ -195,16 +198,37 @@ __device__ __forceinline__ void sts_f2(uint32_t a, float x, float y) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
 }
 
+// One 512-point FFT of v (register-lean core), unfolded into the half spectrum of a real 1024-sequence: one half
+// of an n_fft = 2048 frame.  A force-inlined function, not a lambda: the HalfSpectrum must stay in registers.
+__device__ __forceinline__ void fft512_half_spectrum(float2 (&v)[16], float2 w1, float2 w2, float2 w4, float2 w8,
+                                                     float2* my_tile, int lane, int h, int partner, float2 base1024,
+                                                     HalfSpectrum& out) {
+  __syncwarp();
+  fft512_pass1_pow(v, w1, w2, w4, w8, my_tile, lane);
+  __syncwarp();
+  fft512_pass2(v, my_tile, lane);
+  float2 send[8], recv[8], zlo[8], zhi[8];
+  combine_send(v, h, send);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    recv[j] = make_float2(__shfl_xor_sync(0xffffffffu, send[j].x, 16), __shfl_xor_sync(0xffffffffu, send[j].y, 16));
+  combine_finish(v, recv, h, zlo, zhi);
+  mirror_send512(zlo, zhi, lane, send);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    recv[j] = make_float2(__shfl_sync(0xffffffffu, send[j].x, partner), __shfl_sync(0xffffffffu, send[j].y, partner));
+  unfold_half_spectrum(zlo, zhi, recv, base1024, out);
+}
+
 // OCC = CTAs per SM the instantiation is built for.  OCC == 3 (n_fft 1024, TF 8 only) trades
-// registers and shared memory for a third CTA: window taps and twiddles are not kept in
-// registers (85-register budget) and the waveform tile is single-buffered.
+// registers for a third CTA: window taps and twiddles are not kept in registers (80-register budget).
 template <int NFFT, int TF, int OCC>
 struct FusedLayout {
   // n_fft 2048 with OCC == 2 runs each frame as two 512-point FFTs (even / odd samples) on the
   // register-lean core; with OCC == 1 it is the 32-points-per-lane form (fallback when the lean
   // layout does not fit twice into an SM).
   static constexpr bool kSplit2048 = NFFT == 2048 && OCC == 2;
-  static constexpr int kWaveBufs = (OCC == 3 || kSplit2048) ? 1 : 2;
+  static constexpr int kWaveBufs = 1;  // the next tile is copied in under this tile's mel phase
   static constexpr bool kWindowInSmem = NFFT == 2048 || OCC == 3;
   static constexpr int kBins = NFFT / 2 + 1;
   static constexpr bool kTile512 = NFFT == 1024 || kSplit2048;
@@ -235,11 +259,15 @@ struct FusedLayout {
   // n_chan = channel count padded to the group size.  The records follow the weights, so the mel loop's
   // one-step read-ahead past the last span stays inside the allocation.
   static __host__ __device__ size_t rec_off(int wave_len, int nnz) { return align16(weights_off(wave_len) + size_t(nnz) * 4); }
-  static __host__ __device__ size_t bar_off(int wave_len, int n_chan, int nnz) {
+  static __host__ __device__ size_t order_off(int wave_len, int n_chan, int nnz) {
     return align16(rec_off(wave_len, nnz) + size_t(n_chan) * sizeof(ChanRec));
   }
-  static __host__ __device__ size_t total(int wave_len, int n_chan, int nnz) {
-    return bar_off(wave_len, n_chan, nnz) + 64;  // two mbarriers (16 B), the next tile's description (32 B), spare
+  // n_order = entries of the group-order table
+  static __host__ __device__ size_t bar_off(int wave_len, int n_chan, int nnz, int n_order) {
+    return align16(order_off(wave_len, n_chan, nnz) + size_t(n_order) * 4);
+  }
+  static __host__ __device__ size_t total(int wave_len, int n_chan, int nnz, int n_order) {
+    return bar_off(wave_len, n_chan, nnz, n_order) + 48;  // one mbarrier (16 B with padding), the next tile's description (32 B)
   }
 };
 
@@ -285,10 +313,11 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
   float2* s_fold = reinterpret_cast<float2*>(smem + p.off_fold);
   float* s_weights = reinterpret_cast<float*>(smem + p.off_weights);
   ChanRec* s_rec = reinterpret_cast<ChanRec*>(smem + p.off_rec);
+  int* s_order = reinterpret_cast<int*>(smem + p.off_order);
   // 32-bit shared addresses of the regions the mel phase and the bookkeeping touch
   const uint32_t sa_base = smem_u32(smem);
   const uint32_t sa_bar = sa_base + p.off_bars;   // bars[0], bars[1] at +0, +8
-  const uint32_t sa_slot = sa_bar + 16;           // {next tile, row, t0, n_valid}, {frame_limit, bulk_lo, bulk_n, manual}
+  const uint32_t sa_slot = sa_bar + 16;           // the next tile: {tile, row, t0, n_valid}, {frame_limit, bulk_lo, bulk_n, manual}
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -298,7 +327,6 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
 
   if (tid == 0) {
     mbar_init(sa_bar, 1);
-    mbar_init(sa_bar + 8, 1);
     fence_mbar_init();
   }
 
@@ -336,9 +364,9 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
 
   const bool hop_even = (p.hop & 1) == 0;
   unsigned long long edge_hits = 0;
-  uint32_t phase_bits = 0;  // bit b: parity to wait for on bars[b]
+  uint32_t wave_parity = 0;  // parity to wait for on the waveform barrier
 
-  // Where tile `tile` sits and how its samples reach shared memory.  Two multiply-high divisions and a page of
+  // Where tile `tile` sits and how its samples reach shared memory.  Two multiply-high divisions and some
   // integer logic: evaluated by one thread per tile.
   auto describe = [&](int tile) {
     TileInfo ti;
@@ -357,28 +385,39 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
     const int b0 = s0 - p.src_base;                                          // where that sample sits in the buffer
     ti.src0 = (long long)ti.row * p.row_stride + b0;
     constexpr int kA = kAlign - 1;
-    int lo = s0 < 0 ? ((-s0 + kA) & ~kA) : 0;                                 // first wave index with a real sample
-    if (b0 + lo < 0) lo = (-b0 + kA) & ~kA;                                   // ... that is resident in the buffer
-    int hi = p.n_samples - s0 < p.wave_len ? ((p.n_samples - s0) & ~kA) : p.wave_len;  // one past the last
-    const bool row_vec_ok = ((reinterpret_cast<uintptr_t>(p.wav) & 15) == 0) && ((p.row_stride & (kAlign - 1)) == 0);
-    const bool can_bulk = row_vec_ok && p.pad_outer == 0 && (b0 & kA) == 0 && hi > lo;
-    ti.bulk_lo = can_bulk ? lo : 0;
-    ti.bulk_n = can_bulk ? hi - lo : 0;
-    ti.manual = (!can_bulk || lo > 0 || hi < p.wave_len) ? 1 : 0;
+    if (p.bulk_ok && s0 >= 0 && b0 >= 0 && (b0 & kA) == 0 && s0 + p.wave_len <= p.n_samples) {
+      ti.bulk_lo = 0;  // interior tile (all but one or two per row): one copy brings everything
+      ti.bulk_n = p.wave_len;
+      ti.manual = 0;
+    } else {
+      int lo = s0 < 0 ? ((-s0 + kA) & ~kA) : 0;                                 // first wave index with a real sample
+      if (b0 + lo < 0) lo = (-b0 + kA) & ~kA;                                   // ... that is resident in the buffer
+      int hi = p.n_samples - s0 < p.wave_len ? ((p.n_samples - s0) & ~kA) : p.wave_len;  // one past the last
+      const bool can_bulk = p.bulk_ok && (b0 & kA) == 0 && hi > lo;
+      ti.bulk_lo = can_bulk ? lo : 0;
+      ti.bulk_n = can_bulk ? hi - lo : 0;
+      ti.manual = (!can_bulk || lo > 0 || hi < p.wave_len) ? 1 : 0;
+    }
     return ti;
   };
-  // thread 0: start the bulk async copy of a tile into wave buffer b
-  auto stage_bulk = [&](const TileInfo& ti, int b) {
+  // thread 0: start the bulk async copy of a tile into the wave buffer
+  auto stage_bulk = [&](const TileInfo& ti) {
     if (ti.frame_limit == 0 || ti.bulk_n == 0 || DMEL_SKIP(p, 4)) return;
-    const uint32_t dst = sa_base + p.off_wave + (uint32_t)(b * p.wave_len + ti.bulk_lo) * (uint32_t)sizeof(wave_t);
+    const uint32_t dst = sa_base + p.off_wave + (uint32_t)ti.bulk_lo * (uint32_t)sizeof(wave_t);
     fence_proxy_async();  // earlier generic-proxy reads of this buffer are ordered before the async write
-    mbar_expect_tx(sa_bar + 8 * b, ti.bulk_n * (int)sizeof(wave_t));
-    bulk_copy_g2s(dst, wav + ti.src0 + ti.bulk_lo, ti.bulk_n * (int)sizeof(wave_t), sa_bar + 8 * b);
+    mbar_expect_tx(sa_bar, ti.bulk_n * (int)sizeof(wave_t));
+    bulk_copy_g2s(dst, wav + ti.src0 + ti.bulk_lo, ti.bulk_n * (int)sizeof(wave_t), sa_bar);
+  };
+  // thread 0: leave the description of the next tile (or "no more tiles") in the slot
+  auto post = [&](int tile, const TileInfo& ti) {
+    const bool any = tile < p.n_tiles;
+    sts_i4(sa_slot, make_int4(tile, any ? ti.row : 0, any ? ti.t0 : 0, any ? ti.n_valid : 0));
+    sts_i4(sa_slot + 16, make_int4(any ? ti.frame_limit : 0, any ? ti.bulk_lo : 0, any ? ti.bulk_n : 0, any ? ti.manual : 0));
   };
   // all threads: the part of a tile no bulk copy can bring (reflected row ends, unaligned rows)
-  auto stage_manual = [&](int row, int t0, int bulk_lo, int bulk_n, int b) {
+  auto stage_manual = [&](int row, int t0, int bulk_lo, int bulk_n) {
     if (DMEL_SKIP(p, 4)) return;
-    wave_t* wave = wave0 + b * p.wave_len;
+    wave_t* wave = wave0;
     const int padded_len = p.n_samples + 2 * p.pad_inner + 2 * p.pad_outer;
     const wave_t* src = wav + (long long)row * p.row_stride - p.src_base;
     const int j0 = (p.t_begin + t0) * p.hop;  // first position in the padded row
@@ -402,6 +441,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
       s_rec[i].b = __int_as_float(0xff800000);
     }
   }
+  for (int i = tid; i < p.n_order; i += kThreads) s_order[i] = p.group_order[i];
   for (int i = tid; i < p.nnz; i += kThreads) s_weights[i] = p.weights[i];
   if constexpr (!LY::kMagsInTiles) {
     for (int i = tid; i < LY::kMagFloats; i += kThreads) mags[i] = 0.f;  // the 3 pad columns of each row stay zero
@@ -415,11 +455,17 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
     for (int i = tid; i < LY::kFoldN; i += kThreads) s_fold[i] = p.fold_tw[i];
   }
   grid_dependency_wait();  // from here on: the caller's tensors (waveform, lengths, statistics, outputs, tile counter)
+
+  // Tiles: the first is blockIdx.x; later ones come from a global counter (or a static stride when p.sched is
+  // null), claimed ONE tile ahead so that the CTAs of the grid finish within a tile of each other (a tile is
+  // several microseconds of a launch that lasts a hundred: claiming two ahead costs more at the end of the
+  // launch than the deeper prefetch gains).
+  const bool dynamic = p.sched != nullptr;
   int tile = blockIdx.x;
-  TileInfo first = describe(tile < p.n_tiles ? tile : 0);
+  const TileInfo first = describe(tile < p.n_tiles ? tile : 0);
   if (tile < p.n_tiles) {
-    if (tid == 0) stage_bulk(first, 0);  // the first tile leaves HBM while the statistics below are fetched
-    if (first.manual && first.frame_limit) stage_manual(first.row, first.t0, first.bulk_lo, first.bulk_n, 0);
+    if (tid == 0) stage_bulk(first);  // the first tile leaves HBM while the statistics below are fetched
+    if (first.manual && first.frame_limit) stage_manual(first.row, first.t0, first.bulk_lo, first.bulk_n);
   }
   if constexpr (kCodes) {
     for (int i = tid; i < p.n_chan_pad; i += kThreads) {
@@ -429,49 +475,23 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
       if constexpr (kDequant) s_rec[i].c = real ? p.q_step[i] : 0.f;
     }
   }
-  __syncthreads();  // constants + barrier init visible
-  // Tiles after the first are handed out by a global counter (lean variants), so the CTAs of the
-  // grid finish within one tile of each other instead of one or two tiles apart.
-  constexpr bool kDynamic = LY::kWaveBufs == 1;
-  const bool dynamic = kDynamic && p.sched != nullptr;
+  __syncthreads();  // constants, barrier init and the first tile's plain stores visible
 
   // CTA-uniform description of the current tile (every thread holds a copy)
   int cur_row = first.row, cur_t0 = first.t0, cur_valid = first.n_valid, cur_limit = first.frame_limit;
-  int cur_bulk = first.bulk_n;  // (plain-load staging is ordered by the barrier that closes the previous tile)
+  int cur_bulk = first.bulk_n;
 
-  for (int it = 0; tile < p.n_tiles; ++it) {
-    const int b = LY::kWaveBufs == 2 ? (it & 1) : 0;
-    const wave_t* wave = wave0 + b * p.wave_len;
+  while (tile < p.n_tiles) {
+    const wave_t* wave = wave0;
     const bool dead = cur_limit == 0;
 
-    // ---- 1. this tile's samples are in wave[b]
-    if (!dead && !DMEL_SKIP(p, 4)) {
-      if (cur_bulk) {
-        mbar_wait(sa_bar + 8 * b, (phase_bits >> b) & 1u);
-        phase_bits ^= 1u << b;
-      }
+    // ---- 1. this tile's samples are in the wave buffer (plain stores: ordered by the barriers that closed the previous tile)
+    if (!dead && cur_bulk && !DMEL_SKIP(p, 4)) {
+      mbar_wait(sa_bar, wave_parity);
+      wave_parity ^= 1u;
     }
-    // thread 0 finds out which tile comes next and describes it; with two wave buffers its copy starts now
     int fetched = 0;
-    TileInfo nd;
-    nd.bulk_n = 0;
-    nd.frame_limit = 0;
-    if (tid == 0) {
-      if constexpr (kDynamic) {
-        if (dynamic) fetched = atomicAdd(p.sched, 1);  // consumed after the FFT: its latency is never waited for
-      } else {
-        const int next_tile = tile + (int)gridDim.x;
-        int4 s0 = make_int4(next_tile, 0, 0, 0), s1 = make_int4(0, 0, 0, 0);
-        if (next_tile < p.n_tiles) {
-          nd = describe(next_tile);
-          stage_bulk(nd, b ^ 1);  // double buffered: the next tile loads while this one computes
-          s0 = make_int4(next_tile, nd.row, nd.t0, nd.n_valid);
-          s1 = make_int4(nd.frame_limit, nd.bulk_lo, nd.bulk_n, nd.manual);
-        }
-        sts_i4(sa_slot, s0);
-        sts_i4(sa_slot + 16, s1);
-      }
-    }
+    if (dynamic && tid == 0) fetched = atomicAdd(p.sched, 1);  // consumed after the FFT barrier: its latency is never waited for
 
     // ---- 2. FFT -> magnitudes ------------------------------------------------
     const int fft_frames = DMEL_SKIP(p, 1) ? 0 : cur_limit;
@@ -527,24 +547,6 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
     } else if constexpr (kSplit) {
       const int h = lane >> 4;
       const int partner = mirror_lane512(lane);
-      // one 512-point FFT of v, unfolded into the half spectrum of a real 1024-sequence
-      auto half = [&](float2 (&v)[16], HalfSpectrum& out) {
-        __syncwarp();
-        fft512_pass1_pow(v, w1, w2, w4, w8, my_tile, lane);
-        __syncwarp();
-        fft512_pass2(v, my_tile, lane);
-        float2 send[8], recv[8], zlo[8], zhi[8];
-        combine_send(v, h, send);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          recv[j] = make_float2(__shfl_xor_sync(0xffffffffu, send[j].x, 16), __shfl_xor_sync(0xffffffffu, send[j].y, 16));
-        combine_finish(v, recv, h, zlo, zhi);
-        mirror_send512(zlo, zhi, lane, send);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          recv[j] = make_float2(__shfl_sync(0xffffffffu, send[j].x, partner), __shfl_sync(0xffffffffu, send[j].y, partner));
-        unfold_half_spectrum(zlo, zhi, recv, base1024, out);
-      };
       const bool hop_vec = (p.hop & 3) == 0;
       const float4* win4 = reinterpret_cast<const float4*>(s_window) + lane;
 #pragma unroll 1
@@ -571,8 +573,8 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
           }
         }
         HalfSpectrum e, o;
-        half(v, e);
-        half(odd, o);
+        fft512_half_spectrum(v, w1, w2, w4, w8, my_tile, lane, h, partner, base1024, e);
+        fft512_half_spectrum(odd, w1, w2, w4, w8, my_tile, lane, h, partner, base1024, o);
         float* mrow = LY::kMagsInTiles ? reinterpret_cast<float*>(my_tile) : mags + fr * kPitch;
         combine2048_store(e, o, base2048, mrow, lane);
         if constexpr (LY::kMagsInTiles) {
@@ -614,40 +616,33 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
         }
       }
     }
-    if constexpr (kDynamic) {
-      if (tid == 0) {  // describe the next tile (one thread: the others only read the result)
-        const int next_tile = dynamic ? (int)gridDim.x + fetched : tile + (int)gridDim.x;
-        int4 s0 = make_int4(next_tile, 0, 0, 0), s1 = make_int4(0, 0, 0, 0);
-        if (next_tile < p.n_tiles) {
-          nd = describe(next_tile);
-          s0 = make_int4(next_tile, nd.row, nd.t0, nd.n_valid);
-          s1 = make_int4(nd.frame_limit, nd.bulk_lo, nd.bulk_n, nd.manual);
-        }
-        sts_i4(sa_slot, s0);
-        sts_i4(sa_slot + 16, s1);
+    __syncthreads();  // magnitudes complete, the wave buffer is free
+    // One thread finds out which tile comes next, describes it and starts its copy, which flies under the mel
+    // phase; that thread's warp carries the lightest share of the mel phase to make up for it.
+    if (tid == 0) {
+      const int next_tile = dynamic ? (int)gridDim.x + fetched : tile + (int)gridDim.x;
+      TileInfo nd = first;
+      if (next_tile < p.n_tiles) {
+        nd = describe(next_tile);
+        stage_bulk(nd);
       }
+      post(next_tile, nd);
     }
-    __syncthreads();  // magnitudes complete, wave[b] free, the slot describes the next tile
-    if constexpr (LY::kWaveBufs == 1) {
-      if (tid == 0) stage_bulk(nd, 0);  // single buffer: it is free now, the copy flies under the mel phase
-    }
-    const int4 nx0 = lds_i4(sa_slot), nx1 = lds_i4(sa_slot + 16);
-    const int next_tile = nx0.x;
-    if (next_tile < p.n_tiles && nx1.w && nx1.x)
-      stage_manual(nx0.y, nx0.z, nx1.y, nx1.z, LY::kWaveBufs == 2 ? (b ^ 1) : 0);
 
     // ---- 3. mel filterbank, log, quantise --------------------------------
-    // One lane per frame, 32/TF adjacent channels side by side in a warp.  The host pads the spans
-    // of such a channel group to one common length, so the bin loop is warp-uniform.
+    // One lane per frame and PAIR of channels (m, m + 32/TF): a group of 2 * 32/TF adjacent channels side by
+    // side in a warp.  The host pads the spans of a group to one common length and interleaves the weights of
+    // a pair step by step, so the bin loop is warp-uniform and serves two independent accumulation chains; it
+    // also deals the groups to the warps so that every warp gets about the same number of steps.
     if (!DMEL_SKIP(p, 2)) {
       constexpr int kGroups = 32 / TF;
-      constexpr int kStep = kWarps * kGroups;  // channels between two trips of a lane
+      constexpr int kChanIter = 2 * kGroups;        // channels of a group
+      constexpr int kRecB = kGroups * (int)sizeof(ChanRec);  // record of the pair's second channel
       const int fr = lane % TF;
       const int sub = lane / TF;
       const int t = cur_t0 + fr;
-      const int m0 = warp * kGroups + sub;
-      const size_t ostep = (size_t)kStep * p.n_frames;
-      size_t o = ((size_t)cur_row * p.n_mels + m0) * p.n_frames + t;
+      const size_t opair = (size_t)kGroups * p.n_frames;  // from a pair's first channel to its second
+      const size_t obase = (size_t)cur_row * p.n_mels * p.n_frames + t;
       auto store_logmel = [&](size_t at, float v) {
         if constexpr (kBf16) reinterpret_cast<__nv_bfloat16*>(p.logmel)[at] = __float2bfloat16_rn(v);
         else p.logmel[at] = v;
@@ -657,137 +652,120 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
         if constexpr (kCodes || kLogmel) {
           const bool in_row = t < p.n_frames;
 #pragma unroll 1
-          for (int m = m0; m < p.n_mels; m += kStep, o += ostep)
+          for (int m = warp * kGroups + sub; m < p.n_mels; m += kWarps * kGroups) {
+            const size_t od = obase + (size_t)m * p.n_frames;
             if (in_row) {
-              if constexpr (kCodes) p.codes[o] = 0;
-              if constexpr (kDequant) p.dequant[o] = 0.f;
-              if constexpr (kLogmel) store_logmel(o, 0.f);
+              if constexpr (kCodes) p.codes[od] = 0;
+              if constexpr (kDequant) p.dequant[od] = 0.f;
+              if constexpr (kLogmel) store_logmel(od, 0.f);
             }
+          }
         }
       } else {
         const uint32_t xrow = sa_base + p.off_mags + (uint32_t)fr * (kPitch * 4);
         const uint32_t wbase = sa_base + p.off_weights;
-        uint32_t rec = sa_base + p.off_rec + (uint32_t)m0 * (uint32_t)sizeof(ChanRec);
-        // A tile is `full` when all TF frames are valid frames of the row and no phantom channel pads a group:
-        // the common case, and the one whose epilogue carries no predicates.
-        const bool full = (cur_t0 + TF <= cur_valid) && (p.n_chan_pad == p.n_mels);
-        // banded dot product of this lane's frame with the channel the record describes
-        auto channel_value = [&](const int4& c) {
-          uint32_t wa = wbase + c.y, xa = xrow + c.x;
-          const uint32_t xe = xa + c.z;
-          float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 1
-          do {
-            const float4 w = lds_f4(wa);
-            const float4 x = lds_f4(xa);
-            wa += 16;
-            xa += 16;
-            acc0 = fmaf(w.x, x.x, acc0);
-            acc1 = fmaf(w.y, x.y, acc1);
-            acc0 = fmaf(w.z, x.z, acc0);
-            acc1 = fmaf(w.w, x.w, acc1);
-          } while (xa != xe);
-          return fast_log(fmaxf(acc0 + acc1, kLogClip));
+        const uint32_t rec0 = sa_base + p.off_rec + (uint32_t)sub * (uint32_t)sizeof(ChanRec);
+        const bool in_row = t < p.n_frames;
+        const bool valid = t < cur_valid;
+        // everything that happens to one channel's value.  kFull: all TF frames of the tile are valid frames of
+        // the row and no phantom channel pads a group - the common case, whose epilogue carries no predicates.
+        auto emit = [&]<bool kFull>(std::bool_constant<kFull>, float value, const float4& q, uint32_t rec_at, int m, size_t at) {
+          const bool live = kFull || m < p.n_mels;
+          const bool ok = kFull || (live && in_row);
+          const bool val = kFull || valid;
+          if constexpr (kLogmel) {
+            const float out = (!kFull && p.mask_invalid && !val) ? 0.f : value;
+            if (ok) store_logmel(at, out);
+            if (p.row_sum) {  // per (row, channel) sum over time: the caller's mels.mean(-1) without another pass
+              float part = ok ? out : 0.f;
+#pragma unroll
+              for (int d = TF / 2; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+              if (fr == 0 && live) atomicAdd(p.row_sum + (size_t)cur_row * p.n_mels + m, part);
+            }
+          }
+          if constexpr (kCodes) {
+            const float pos = __fmul_rn(__fsub_rn(value, q.x), q.y);
+            const float qf = fminf(fmaxf(floorf(pos), 0.f), p.kmax);
+            if (ok) p.codes[at] = val ? (unsigned char)qf : (unsigned char)0;
+            if constexpr (kDequant) {  // the table entry the stand-alone decoder would look up, same two roundings
+              const float centre = __fadd_rn(q.x, __fmul_rn(qf + 0.5f, q.z));
+              if (ok) p.dequant[at] = val ? centre : 0.f;
+            }
+            if constexpr (kEdge) {
+              const float e = fminf(fmaxf(rintf(pos), 1.f), p.kmax);
+              if (live && val && fabsf(pos - e) < p.edge_eps * q.y) ++edge_hits;
+            }
+          }
+          if constexpr (kStats) {
+            float lo = (val && live) ? value : __int_as_float(0x7f800000);
+            float hi = (val && live) ? value : __int_as_float(0xff800000);
+#pragma unroll
+            for (int d = TF / 2; d >= 1; d >>= 1) {
+              lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+              hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+            }
+            if (fr == 0 && live) sts_f2(rec_at + 16, fminf(q.x, lo), fmaxf(q.y, hi));  // channel m always belongs to this lane of this warp: no race
+          }
         };
-        if (full) {
+        auto sweep = [&](auto full_tag) {
 #pragma unroll 1
-          for (int mb = warp * kGroups; mb < p.n_chan_pad; mb += kStep, rec += kStep * (int)sizeof(ChanRec), o += ostep) {
-            const int4 c = lds_i4(rec);
-            const float4 q = lds_f4(rec + 16);
-            const float value = channel_value(c);
-            if constexpr (kLogmel) {
-              store_logmel(o, value);
-              if (p.row_sum) {  // per (row, channel) sum over time: the caller's mels.mean(-1) without another pass
-                float part = value;
-#pragma unroll
-                for (int d = TF / 2; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-                if (fr == 0) atomicAdd(p.row_sum + (size_t)cur_row * p.n_mels + mb + sub, part);
-              }
-            }
-            if constexpr (kCodes) {
-              const float pos = __fmul_rn(__fsub_rn(value, q.x), q.y);
-              const float qf = fminf(fmaxf(floorf(pos), 0.f), p.kmax);
-              p.codes[o] = (unsigned char)qf;
-              if constexpr (kDequant)  // the table entry the stand-alone decoder would look up, same two roundings
-                p.dequant[o] = __fadd_rn(q.x, __fmul_rn(qf + 0.5f, q.z));
-              if constexpr (kEdge) {
-                const float e = fminf(fmaxf(rintf(pos), 1.f), p.kmax);
-                if (fabsf(pos - e) < p.edge_eps * q.y) ++edge_hits;
-              }
-            }
-            if constexpr (kStats) {
-              float lo = value, hi = value;
-#pragma unroll
-              for (int d = TF / 2; d >= 1; d >>= 1) {
-                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
-              }
-              if (fr == 0) sts_f2(rec + 16, fminf(q.x, lo), fmaxf(q.y, hi));  // channel m always belongs to this lane of this warp: no race
-            }
-          }
-        } else {
-          const bool in_row = t < p.n_frames;
-          const bool valid = t < cur_valid;
+          for (int k = warp; k < p.n_order; k += kWarps) {
+            const int g = s_order[k];
+            if (g < 0) continue;  // (warp-uniform)
+            const int m = g * kChanIter + sub;
+            const uint32_t rec = rec0 + (uint32_t)g * (kChanIter * (int)sizeof(ChanRec));
+            const size_t o = obase + (size_t)m * p.n_frames;
+            const int4 ca = lds_i4(rec), cb = lds_i4(rec + kRecB);
+            const float4 qa = lds_f4(rec + 16), qb = lds_f4(rec + kRecB + 16);
+            // banded dot products of this lane's frame with the two channels: same span length, weights interleaved
+            uint32_t wa = wbase + ca.y, xa = xrow + ca.x, xb = xrow + cb.x;
+            const uint32_t xe = xa + ca.z;
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll 1
-          for (int mb = warp * kGroups; mb < p.n_chan_pad; mb += kStep, rec += kStep * (int)sizeof(ChanRec), o += ostep) {
-            const int m = mb + sub;
-            const bool live = m < p.n_mels;
-            const int4 c = lds_i4(rec);
-            const float4 q = lds_f4(rec + 16);
-            const float value = channel_value(c);
-            if constexpr (kLogmel) {
-              const float out = (p.mask_invalid && !valid) ? 0.f : value;
-              if (live && in_row) store_logmel(o, out);
-              if (p.row_sum) {
-                float part = (live && in_row) ? out : 0.f;
-#pragma unroll
-                for (int d = TF / 2; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-                if (fr == 0 && live) atomicAdd(p.row_sum + (size_t)cur_row * p.n_mels + m, part);
-              }
-            }
-            if constexpr (kCodes) {
-              const float pos = __fmul_rn(__fsub_rn(value, q.x), q.y);
-              const float qf = fminf(fmaxf(floorf(pos), 0.f), p.kmax);
-              if (live && in_row) p.codes[o] = valid ? (unsigned char)qf : (unsigned char)0;
-              if constexpr (kDequant) {
-                const float centre = __fadd_rn(q.x, __fmul_rn(qf + 0.5f, q.z));
-                if (live && in_row) p.dequant[o] = valid ? centre : 0.f;
-              }
-              if constexpr (kEdge) {
-                const float e = fminf(fmaxf(rintf(pos), 1.f), p.kmax);
-                if (live && valid && fabsf(pos - e) < p.edge_eps * q.y) ++edge_hits;
-              }
-            }
-            if constexpr (kStats) {
-              float lo = (valid && live) ? value : __int_as_float(0x7f800000);
-              float hi = (valid && live) ? value : __int_as_float(0xff800000);
-#pragma unroll
-              for (int d = TF / 2; d >= 1; d >>= 1) {
-                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
-              }
-              if (fr == 0 && live) sts_f2(rec + 16, fminf(q.x, lo), fmaxf(q.y, hi));
-            }
+            do {
+              const float4 wA = lds_f4(wa), wB = lds_f4(wa + 16);
+              const float4 xA = lds_f4(xa), xB = lds_f4(xb);
+              wa += 32;
+              xa += 16;
+              xb += 16;
+              a0 = fmaf(wA.x, xA.x, a0);
+              b0 = fmaf(wB.x, xB.x, b0);
+              a1 = fmaf(wA.y, xA.y, a1);
+              b1 = fmaf(wB.y, xB.y, b1);
+              a0 = fmaf(wA.z, xA.z, a0);
+              b0 = fmaf(wB.z, xB.z, b0);
+              a1 = fmaf(wA.w, xA.w, a1);
+              b1 = fmaf(wB.w, xB.w, b1);
+            } while (xa != xe);
+            const float va = fast_log(fmaxf(a0 + a1, kLogClip));
+            const float vb = fast_log(fmaxf(b0 + b1, kLogClip));
+            emit(full_tag, va, qa, rec, m, o);
+            emit(full_tag, vb, qb, rec + kRecB, m + kGroups, o + opair);
           }
-        }
+        };
+        if ((cur_t0 + TF <= cur_valid) && (p.n_chan_pad == p.n_mels)) sweep(std::true_type{});
+        else sweep(std::false_type{});
       }
     }
-    __syncthreads();  // magnitudes and the slot are free again; manual stores of the next tile are visible
-    tile = next_tile;
+    __syncthreads();  // magnitudes are free again; the slot describes the next tile
+    const int4 nx0 = lds_i4(sa_slot), nx1 = lds_i4(sa_slot + 16);
+    tile = nx0.x;
     cur_row = nx0.y;
     cur_t0 = nx0.z;
     cur_valid = nx0.w;
     cur_limit = nx1.x;
     cur_bulk = nx1.z;
+    if (tile < p.n_tiles && nx1.w && nx1.x) {  // a row end: stage what no bulk copy could bring (a few tiles per row)
+      stage_manual(nx0.y, nx0.z, nx1.y, nx1.z);
+      __syncthreads();
+    }
   }
-  if constexpr (kDynamic) {
-    // the last CTA to finish leaves both counters at zero for the next launch
-    if (dynamic && tid == 0) {
-      __threadfence();
-      if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
-        atomicExch(p.sched, 0);
-        atomicExch(p.sched + 1, 0);
-      }
+  // the last CTA to finish leaves both counters at zero for the next launch
+  if (dynamic && tid == 0) {
+    __threadfence();
+    if (atomicAdd(p.sched + 1, 1) == (int)gridDim.x - 1) {
+      atomicExch(p.sched, 0);
+      atomicExch(p.sched + 1, 0);
     }
   }
 

@@ -34,8 +34,9 @@ def main():
     wx = h.index("L1 Wavefronts Shared Excessive")
     with tempfile.TemporaryDirectory() as td:
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=td, capture_output=True)
-        cubin = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
-        dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cubin)], capture_output=True, text=True).stdout
+        # one cubin per translation unit of the library: disassemble them all, the kernel filter below picks
+        dis = "".join(subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, f)], capture_output=True, text=True).stdout
+                      for f in sorted(os.listdir(td)) if f.endswith(".cubin"))
     lines, cur, active = [], None, False
     for ln in dis.splitlines():
         if ln.startswith("//---") and ".text." in ln:
