@@ -6,15 +6,21 @@
 One "step" = one pass of the hot path over one batch of BASELINE configs[1]:
 64 utterances x 10 s, 24 kHz, n_fft 1024, hop 256, 128 mel, 16 bins —
 encode (waveform -> uint8 codes) and dequantise (codes -> mel) in ONE fused launch (the quantiser's
-forward, ``DMelTokenizer.encode_decode``); a separate pass times the stand-alone encode and
-dequantise kernels for the roofline entries.
-With N GPUs every rank runs that batch on its own shard of utterances (weak
-scaling, no data-path collective; the calibration all-reduce happens once,
-before the timed region).  Prints ONE JSON line on rank 0.
+forward, ``DMelTokenizer.encode_decode``).  The K-step window is timed between two CUDA events and repeated
+(``repetitions`` in the line, at least 30); ``value`` comes from the MEDIAN window, so one straggling window of
+a 2 ms measurement cannot set the number.  A separate pass times single launches for the roofline entries.
+With N GPUs every rank runs that batch on its own shard of utterances (weak scaling, no data-path collective).
 
-``--impl reference`` times the CPU oracle port of the reference's torch path
-(oracle/dmel_oracle.py; the reference is Python, so there is no oracle/_ref)
-on the host cores for the same batch.
+After the headline region the default run measures, under ``secondary``, every other BASELINE config through
+the same library: configs[2] (dataset calibrate + encode, sharded, the NCCL all-reduce INSIDE the timed region),
+configs[3] (streaming, per-chunk latency), configs[4] (long-form n_fft 2048), and the stand-alone quantiser
+kernels at a size where HBM binds.  ``torch_gpu_baseline`` is the reference's own file on CUDA tensors on this
+GPU (the stock-op chain the fused kernel replaces: cuFFT + cuBLAS + elementwise kernels).
+
+``--impl reference`` runs the reference's own, unmodified ``dmel_codec/utils/spectrogram.py`` (pip-installed
+into ``baseline/_ref`` by ``__graft_entry__.build()``; ``librosa.filters.mel``, which cannot be installed
+offline, is stood in for) on all host cores, followed by the quantiser spec in plain torch ops — the reference
+has no quantiser.  If ``baseline/_ref`` is absent it falls back to the oracle port and says so (``kind``).
 """
 from __future__ import annotations
 
@@ -107,45 +113,102 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_step(wav, cfg, bank, lo, hi):
-    from oracle import dmel_oracle as O
-    codes = O.dmel_encode(O.log_mel(wav, cfg, bank), lo, hi, N_BINS)
-    return O.dmel_decode(codes, lo, hi, N_BINS)
+def config_block():
+    """Identical in both arms, so the driver's same-config check compares like with like."""
+    return {"workload": WORKLOAD, "per_gpu_batch": f"{BATCH}x{SECONDS}s", "sample_rate": SAMPLE_RATE,
+            "n_fft": GEOM["n_fft"], "hop": GEOM["hop_length"], "n_mels": GEOM["n_mels"], "n_bins": N_BINS}
 
 
-def cpu_oracle_setup(rows: int):
+def torch_quantizer_forward(mel, lo, scale, step, n_bins):
+    """The quantiser spec in stock torch ops: what a user without this library would
+    write after the reference's mel transform.  Used by the two baselines only, never by the product."""
+    codes = torch.clamp(torch.floor((mel - lo[None, :, None]) * scale[None, :, None]), 0, n_bins - 1).to(torch.uint8)
+    return codes, lo[None, :, None] + (codes.to(torch.float32) + 0.5) * step[None, :, None]
+
+
+def torch_stats(mel, n_bins):
+    lo, hi = mel.amin(dim=(0, 2)), mel.amax(dim=(0, 2))
+    width = hi - lo
+    scale = torch.where(width > 0, n_bins / width, torch.zeros_like(width))
+    return lo, scale, width / n_bins
+
+
+def reference_transform(mel_fn):
+    """(transform, kind): the reference's own LogMelSpectrogram from baseline/_ref, or None when it is absent."""
+    from baseline import ref_arm
+    if not ref_arm.available():
+        return None
+    mod = ref_arm.load(mel_fn)
+    return mod.LogMelSpectrogram(sample_rate=SAMPLE_RATE, n_fft=GEOM["n_fft"], win_length=GEOM["win_length"],
+                                 hop_length=GEOM["hop_length"], n_mels=GEOM["n_mels"], f_min=GEOM["f_min"],
+                                 f_max=GEOM["f_max"])
+
+
+def cpu_reference_runner():
+    """-> (step(wav) callable, setup(rows) -> wav, kind, description).  The reference arm's step: the reference's
+    own transform (unmodified file) + the quantiser spec in torch ops; the oracle port only if baseline/_ref is
+    missing."""
     from dmel_codec_b200 import synth
-    from oracle import dmel_oracle as O
-    cfg = O.MelConfig(**GEOM)
-    bank = torch.from_numpy(O.slaney_filterbank(SAMPLE_RATE, GEOM["n_fft"], GEOM["n_mels"], GEOM["f_min"], GEOM["f_max"]))
-    wav = synth.batch(range(rows), N_SAMPLES, SAMPLE_RATE, "speech")
-    lo, hi = O.calibrate_minmax(O.log_mel(wav[: min(rows, 4)], cfg, bank))
-    return wav, cfg, bank, lo, hi
+    from oracle import dmel_oracle as O  # test infrastructure; allowed in the reference arm / cpu_baseline leg only
+
+    ref = reference_transform(O.slaney_filterbank)
+    if ref is not None:
+        state = {}
+
+        def step(wav):
+            with torch.no_grad():
+                mel = ref(wav)
+                if not state:
+                    state["stats"] = torch_stats(mel[:4], N_BINS)
+                return torch_quantizer_forward(mel, *state["stats"], N_BINS)
+
+        kind = "reference"
+        what = ("reference dmel_codec/utils/spectrogram.py (unmodified, baseline/_ref) + Appendix-B quantiser in torch ops; "
+                "librosa.filters.mel stood in for")
+    else:
+        cfg = O.MelConfig(**GEOM)
+        bank = torch.from_numpy(O.slaney_filterbank(SAMPLE_RATE, GEOM["n_fft"], GEOM["n_mels"], GEOM["f_min"], GEOM["f_max"]))
+        state = {}
+
+        def step(wav):
+            mel = O.log_mel(wav, cfg, bank)
+            if not state:
+                state["stats"] = O.calibrate_minmax(mel[:4])
+            lo, hi = state["stats"]
+            codes = O.dmel_encode(mel, lo, hi, N_BINS)
+            return codes, O.dmel_decode(codes, lo, hi, N_BINS)
+
+        kind = "port"
+        what = "oracle/dmel_oracle.py port of the reference's torch path (baseline/_ref absent)"
+
+    def setup(rows):
+        return synth.batch(range(rows), N_SAMPLES, SAMPLE_RATE, "speech")
+
+    return step, setup, kind, what
 
 
 def run_reference(args, rank: int):
-    """The reference's CPU path (oracle port) on the host cores, same batch."""
+    """The reference's CPU path on the host cores, same batch (rank 0 only; other ranks exit without work)."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    wav, cfg, bank, lo, hi = cpu_oracle_setup(BATCH)
+    step, setup, kind, what = cpu_reference_runner()
+    wav = setup(BATCH)
     steps = min(args.steps, 100)  # each step is a full 64 x 10 s batch on the CPU (~0.1 s): bounded
-    args.steps = steps
-    for _ in range(min(args.warmup, 3)):
-        oracle_step(wav, cfg, bank, lo, hi)
+    for _ in range(max(1, min(args.warmup, 3))):
+        step(wav)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle_step(wav, cfg, bank, lo, hi)
+    for _ in range(steps):
+        step(wav)
     dt = time.perf_counter() - t0
-    value = AUDIO_SEC_PER_BATCH * args.steps / dt
-    sample = f"{BATCH} x {SECONDS} s per step, {args.steps} steps, torch {torch.__version__} CPU ops, {cores} threads"
+    value = AUDIO_SEC_PER_BATCH * steps / dt
+    sample = f"{BATCH} x {SECONDS} s per step, {steps} steps, {what}; torch {torch.__version__} CPU, {cores} threads"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU oracle port of reference utils/spectrogram.py + Appendix-B quantiser"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_block(),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -185,10 +248,42 @@ def pin_to_gpu_numa_node(local_rank: int):
     return None
 
 
+REPETITIONS = 30  # K-step windows timed back to back; the headline is the median window
+
+
+def median_window_ms(run_window, reps: int, stream) -> list:
+    """Device time of `reps` windows, each between its own pair of CUDA events (events only BETWEEN windows, so a
+    window is an uninterrupted kernel sequence)."""
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    marks[0].record(stream)
+    for r in range(reps):
+        run_window(r)
+        marks[r + 1].record(stream)
+    torch.cuda.synchronize()
+    return [marks[r].elapsed_time(marks[r + 1]) for r in range(reps)]
+
+
+def time_kernel_ms(fn, reps: int, stream, flush=None) -> float:
+    """Median device time of one call of fn(i), each call between two events; `flush` (if given) runs before every
+    call outside the timed pair to evict the previous call's data from L2."""
+    ms = []
+    for i in range(reps):
+        if flush is not None:
+            flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn(i)
+        e1.record(stream)
+        e1.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return statistics.median(ms)
+
+
 def run_ours(args, rank: int, world: int, local_rank: int):
     import torch.distributed as dist
     import dmel_codec_b200 as d
-    from dmel_codec_b200 import synth
+    from dmel_codec_b200 import filters, synth
+    from dmel_codec_b200 import plan as P
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: dmel_codec_b200 has no CPU path")
@@ -208,153 +303,193 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     lo, scale, table, width = q.lo, q.scale(), q.table(), q.step()
     launch_cfg = plan.describe()
     torch.cuda.synchronize()
-
-    from dmel_codec_b200 import plan as P
     stream = torch.cuda.current_stream(dev)
 
-    def step(i, ev=None):
-        wav = ring[i % RING]
-        if ev is None:  # the benchmark step: codes and dequantised mel from one launch
-            return plan.encode_decode(wav, None, lo, scale, width, N_BINS)
-        ev[0].record(stream)  # probe pass: the step's kernel and the two stand-alone kernels, each between events
-        plan.encode_decode(wav, None, lo, scale, width, N_BINS)
-        ev[1].record(stream)
-        codes = plan.encode(wav, None, lo, scale, N_BINS)
-        ev[2].record(stream)
-        mel = P.dequantize(codes, table)
-        ev[3].record(stream)
-        return codes, mel
+    def step(i):  # the benchmark step: codes and dequantised mel from one launch
+        return plan.encode_decode(ring[i % RING], None, lo, scale, width, N_BINS)
 
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    # per-launch durations (roofline): a separate pass with an event on either side of each kernel, so the timed
-    # region below is an uninterrupted kernel sequence, as in a real pipeline
+    # per-launch durations (roofline): a separate pass with an event on either side of each kernel
     probe = max(3, min(args.steps, 200))
-    events = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(probe)]
-    for i in range(probe):
-        step(i, events[i])
-    torch.cuda.synchronize()
-    fwd_ms = [e[0].elapsed_time(e[1]) for e in events]
-    enc_ms = [e[1].elapsed_time(e[2]) for e in events]
-    deq_ms = [e[2].elapsed_time(e[3]) for e in events]
+    fwd_ms = time_kernel_ms(lambda i: plan.encode_decode(ring[i % RING], None, lo, scale, width, N_BINS), probe, stream)
+    enc_ms = time_kernel_ms(lambda i: plan.encode(ring[i % RING], None, lo, scale, N_BINS), probe, stream)
+    codes0 = plan.encode(ring[0], None, lo, scale, N_BINS)
+    deq_ms = time_kernel_ms(lambda i: P.dequantize(codes0, table), probe, stream)
     if world > 1:
         dist.barrier()
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # ---- the timed region: REPETITIONS windows of exactly K steps, barrier + synchronize on both sides ----------
+    reps = max(REPETITIONS, 1)
     with ClockSampler(local_rank) as clocks:
         torch.cuda.synchronize()
         wall0 = time.perf_counter()
-        t_begin.record(stream)
-        for i in range(args.steps):
-            step(args.warmup + i)
-        t_end.record(stream)
-        torch.cuda.synchronize()
+        windows = median_window_ms(lambda r: [step(args.warmup + r * args.steps + i) for i in range(args.steps)], reps, stream)
         wall = time.perf_counter() - wall0
     if world > 1:
         dist.barrier()
-    total_ms = t_begin.elapsed_time(t_end)  # device time of the K back-to-back steps
-    t = torch.tensor([total_ms, sum(enc_ms) / probe * args.steps, sum(deq_ms) / probe * args.steps, wall * 1e3,
-                      sum(fwd_ms) / probe], dtype=torch.float64, device=dev)
+    t = torch.tensor([statistics.median(windows), min(windows), max(windows), wall * 1e3 / reps, fwd_ms, enc_ms, deq_ms],
+                     dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, enc_total, deq_total, wall_ms, fwd_avg_ms = t.tolist()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every figure is the slowest rank's
+    total_ms, win_min, win_max, wall_ms, fwd_avg_ms, enc_avg_ms, deq_avg_ms = t.tolist()
 
     # ---- end to end through the public API with HOST buffers -------------------
-    e2e_steps = max(3, min(args.steps, 100))  # ~1.4 ms each: long enough to average out host jitter
-    e2e_value = e2e_pcm_value = None
+    e2e = e2e_pcm = None
+    h2d_bytes, d2h_bytes = 4 * BATCH * N_SAMPLES, BATCH * GEOM["n_mels"] * N_FRAMES
     if not args.skip_e2e:
+        e2e_steps = max(3, min(args.steps, 100))  # ~1.3 ms each: long enough to average out host jitter
         host = [ring[r].cpu().pin_memory() for r in range(2)]
         out = torch.empty((BATCH, GEOM["n_mels"], N_FRAMES), dtype=torch.uint8).pin_memory()
-        for r in range(2):
-            tok.encode_host(host[r], out=out)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            tok.encode_host(host[i % 2], out=out)  # returns after codes are in host memory
-        e2e_dt = time.perf_counter() - t0
-        e = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(e, op=dist.ReduceOp.MAX)
-        e2e_value = world * AUDIO_SEC_PER_BATCH * e2e_steps / e.item()
+
+        def timed_calls(bufs):
+            for r in range(2):
+                tok.encode_host(bufs[r], out=out)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                tok.encode_host(bufs[i % 2], out=out)  # returns after the codes are in host memory
+            e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(e, op=dist.ReduceOp.MAX)
+            return e.item() / e2e_steps
+
+        # the raw pinned host->device rate of this box in this run: the floor of any host-buffer call
+        # (best of 12 single copies of the batch, each between its own events)
+        scratch = torch.empty_like(ring[0])
+        best = float("inf")
+        for i in range(14):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            scratch.copy_(host[i % 2], non_blocking=True)
+            c1.record(stream)
+            c1.synchronize()
+            if i >= 2:
+                best = min(best, c0.elapsed_time(c1))
+        h2d_peak = h2d_bytes / (best / 1e3) / 1e9
+        del scratch
+        dt = timed_calls(host)
+        e2e = {"value": world * AUDIO_SEC_PER_BATCH / dt, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "ms_per_call": dt * 1e3,
+               "h2d_gbs": h2d_bytes / dt / 1e9, "h2d_peak_gbs": h2d_peak,
+               "frac_of_h2d_floor": (h2d_bytes / (h2d_peak * 1e9)) / dt,
+               "call": "DMelTokenizer.encode_host -> dmel_encode_host_u8 (pinned host wav in, host codes out); "
+                       "h2d_peak_gbs = raw pinned cudaMemcpyAsync of the same bytes, same run, this rank"}
         # the same call with the waveform as int16 PCM (the format audio is stored in): half the H2D bytes
         host_pcm = [(h.clamp(-1, 1) * 32767.0).round().to(torch.int16).pin_memory() for h in host]
-        for r in range(2):
-            tok.encode_host(host_pcm[r], out=out)
+        dt = timed_calls(host_pcm)
+        e2e_pcm = {"value": world * AUDIO_SEC_PER_BATCH / dt, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes // 2,
+                   "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps, "ms_per_call": dt * 1e3,
+                   "call": "same call with int16 PCM host waveforms (dmel_encode_host_pcm16_u8); secondary line, "
+                           "the reference interface takes float32"}
+        del host, host_pcm, out
+
+    # ---- the stock GPU implementation: the reference's own file on CUDA tensors, same GPU, same batch ----------
+    torch_gpu = None
+    if not args.skip_gpu_baseline:
+        ref = reference_transform(filters.mel_filterbank)
+        if ref is not None:
+            with torch.no_grad():
+                stats = torch_stats(ref(ring[0][:4]), N_BINS)
+
+                def ref_step(i):
+                    return torch_quantizer_forward(ref(ring[i % RING]), *stats, N_BINS)
+
+                for i in range(3):
+                    ref_step(i)
+                k = max(3, min(args.steps, 50))
+                ms = statistics.median(median_window_ms(lambda r: [ref_step(r * k + i) for i in range(k)], 5, stream)) / k
+            g = torch.tensor([ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(g, op=dist.ReduceOp.MAX)
+            torch_gpu = {"value": world * AUDIO_SEC_PER_BATCH / (g.item() / 1e3), "unit": UNIT, "ms_per_step": g.item(),
+                         "what": "reference dmel_codec/utils/spectrogram.py (unmodified, baseline/_ref) on CUDA tensors: reflect pad, "
+                                 "torch.stft (cuFFT), magnitude, matmul (cuBLAS), log-clamp, then the quantiser spec in torch ops; "
+                                 "same batch ring, device-resident, median of 5 windows"}
+        else:
+            torch_gpu = {"value": None, "unavailable": "baseline/_ref absent: run __graft_entry__.build() where /root/reference exists"}
+
+    # ---- the other BASELINE configs, through the same library --------------------------------------------------
+    secondary = None
+    if not args.skip_secondary:
+        del ring
+        torch.cuda.empty_cache()
+        secondary = {}
+        secondary["configs[2]"] = pool_workload("calibrate", rank, world, dev)
+        secondary["configs[4]"] = pool_workload("longform", rank, world, dev)
+        if rank == 0:
+            secondary["configs[3]"] = stream_workload(dev)
+            secondary["kernels"] = standalone_kernels(dev)
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            tok.encode_host(host_pcm[i % 2], out=out)
-        e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(e, op=dist.ReduceOp.MAX)
-        e2e_pcm_value = world * AUDIO_SEC_PER_BATCH * e2e_steps / e.item()
 
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
-    enc_avg_s = enc_total / args.steps / 1e3
-    achieved = ENCODE_BYTES / enc_avg_s / 1e9
-    deq_gbs = DEQUANT_BYTES / (deq_total / args.steps / 1e3) / 1e9
-    traffic = None
+    enc_gbs = ENCODE_BYTES / (enc_avg_ms / 1e3) / 1e9
+    deq_gbs = DEQUANT_BYTES / (deq_avg_ms / 1e3) / 1e9
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "encode_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source", "ncu --set full capture, profiles/encode_traffic.json (not measured in this run)")
 
-    # CPU baseline: the oracle port on this box's host cores, bounded sample
+    # CPU baseline: the reference arm's step on this box's host cores, bounded sample
     cores = os.cpu_count() or 1
-    cpu_value, passes, cpu_dt = None, 0, 0.0
+    cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "skipped"}
     if not args.skip_cpu and world == 1:  # the CPU baseline is a 1-GPU-run line (rank 0, N = 1 only)
         torch.set_num_threads(cores)
-        cwav, cfg, bank, clo, chi = cpu_oracle_setup(BATCH)
-        oracle_step(cwav, cfg, bank, clo, chi)
-        c0 = time.perf_counter()
+        cstep, csetup, kind, what = cpu_reference_runner()
+        cwav = csetup(BATCH)
+        cstep(cwav)
+        passes, c0 = 0, time.perf_counter()
         while passes < 3 or (time.perf_counter() - c0 < 10.0 and passes < 200):
-            oracle_step(cwav, cfg, bank, clo, chi)
+            cstep(cwav)
             passes += 1
         cpu_dt = time.perf_counter() - c0
-        cpu_value = AUDIO_SEC_PER_BATCH * passes / cpu_dt
+        cpu = {"value": AUDIO_SEC_PER_BATCH * passes / cpu_dt, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{passes} passes of the same {BATCH}x{SECONDS}s batch in {cpu_dt:.1f} s: {what}; {cores} threads"}
 
     value = world * AUDIO_SEC_PER_BATCH * args.steps / (total_ms / 1e3)
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": f"{BATCH}x{SECONDS}s", "sharding": "utterances, no data-path collective",
+        "dtype": "f32", "data": "synthetic", "config": config_block(),
+        "timing": {"repetitions": reps, "window_ms_median": total_ms, "window_ms_min": win_min, "window_ms_max": win_max,
+                   "wall_ms_per_window": wall_ms, "sharding": "utterances, no data-path collective",
                    "l2": f"inputs cycle through a ring of {RING} distinct batches ({RING * ENCODE_BYTES / 1e6:.0f} MB > 126 MB L2)",
-                   "timing": "K steps between two CUDA events, no events inside; per-launch durations from a separate pass",
-                   "wall_ms_per_step": wall_ms / args.steps, "rank0_cpu_affinity": affinity},
+                   "method": "each window = K steps between two CUDA events, no events inside; value from the median window, "
+                             "max over ranks; per-launch durations from a separate pass",
+                   "rank0_cpu_affinity": affinity},
         "roofline": {"bound": "hbm", "kernel": f"dmel_fused_kernel<{GEOM['n_fft']},{launch_cfg['tile_frames']},codes+dequant> "
                      f"({launch_cfg['ctas_per_sm']} CTA/SM, {launch_cfg['smem_bytes']} B smem)",
                      "achieved": FORWARD_BYTES / (fwd_avg_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": FORWARD_BYTES / (fwd_avg_ms / 1e3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": FORWARD_BYTES, "avg_launch_ms": fwd_avg_ms,
-                     "note": "the step's kernel, one launch between two events (probe pass). Algorithmic bytes = 4*B*L waveform in "
+                     "frac": FORWARD_BYTES / (fwd_avg_ms / 1e3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": FORWARD_BYTES, "avg_launch_ms": fwd_avg_ms,
+                     "note": "the step's kernel, one launch between two events (probe pass, median). Algorithmic bytes = 4*B*L waveform in "
                              "+ B*M*T codes out + 4*B*M*T dequantised mel out (SURVEY 8d encode + dequant, minus the code re-read)",
-                     "encode_only": {"achieved": achieved, "frac": achieved / peak, "algorithmic_bytes_per_launch": ENCODE_BYTES,
-                                     "avg_launch_ms": enc_avg_s * 1e3},
+                     "encode_only": {"achieved": enc_gbs, "frac": enc_gbs / peak, "algorithmic_bytes_per_launch": ENCODE_BYTES,
+                                     "avg_launch_ms": enc_avg_ms},
                      "dequant": {"achieved": deq_gbs, "frac": deq_gbs / peak, "algorithmic_bytes_per_launch": DEQUANT_BYTES,
-                                 "avg_launch_ms": deq_total / args.steps}},
-        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{passes} passes of the same {BATCH}x{SECONDS}s batch, oracle/dmel_oracle.py, torch CPU, {cores} threads, {cpu_dt:.1f} s"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * BATCH * N_SAMPLES,
-                "d2h_bytes_per_step": BATCH * GEOM["n_mels"] * N_FRAMES, "steps": e2e_steps,
-                "call": "DMelTokenizer.encode_host -> dmel_encode_host_u8 (pinned host wav in, host codes out)"},
-        "e2e_pcm16": {"value": e2e_pcm_value, "unit": UNIT, "h2d_bytes_per_step": 2 * BATCH * N_SAMPLES,
-                      "d2h_bytes_per_step": BATCH * GEOM["n_mels"] * N_FRAMES, "steps": e2e_steps,
-                      "call": "same call with int16 PCM host waveforms (dmel_encode_host_pcm16_u8); secondary line, "
-                              "the reference interface takes float32"},
+                                 "avg_launch_ms": deq_avg_ms,
+                                 "note": "38 MB launch: latency-sized; secondary.kernels has it at a size where HBM binds"}},
+        "cpu_baseline": cpu,
+        "torch_gpu_baseline": torch_gpu,
+        "e2e": e2e if e2e is not None else {"value": None, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+        "e2e_pcm16": e2e_pcm,
+        "secondary": secondary,
         "gpu_launches": args.steps,
         "clocks": clocks.summary(),
     }))
 
 
 # ---------------------------------------------------------------------------
-# secondary workloads (BASELINE configs[2], [3], [4]); not the headline line
+# secondary workloads (BASELINE configs[2], [3], [4]) and stand-alone kernels
 # ---------------------------------------------------------------------------
 def _init_rank():
     rank = int(os.environ.get("RANK", "0"))
@@ -364,11 +499,10 @@ def _init_rank():
     return rank, world, local_rank, torch.device("cuda", local_rank)
 
 
-def run_stream(args):
-    """configs[3]: one stream, 80 ms chunks, 16 kHz / 80 mel: per-chunk latency."""
+def stream_workload(dev):
+    """configs[3]: one stream, 80 ms chunks, 16 kHz / 80 mel: per-chunk latency (host call + stream sync)."""
     import dmel_codec_b200 as d
     from dmel_codec_b200 import synth
-    rank, world, local_rank, dev = _init_rank()
     geom = dict(sample_rate=16000, n_fft=1024, win_length=1024, hop_length=256, n_mels=80)
     tok = d.DMelTokenizer(n_bins=16, **geom).to(dev)
     wav = synth.batch([0], 16000 * 30, 16000, "speech").to(dev)
@@ -386,30 +520,27 @@ def run_stream(args):
                 outs[k] = torch.empty((1, geom["n_mels"], k), dtype=torch.uint8, device=dev)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            codes = enc.push(x, out=outs[k])
+            enc.push(x, out=outs[k])
             torch.cuda.synchronize()
             lat.append((time.perf_counter() - t0) * 1e6)
         enc.flush()
     lat.sort()
     p50, p99 = lat[len(lat) // 2], lat[min(len(lat) - 1, int(len(lat) * 0.99))]
-    print(json.dumps({"metric": "dmel_stream_chunk_latency_us", "value": p50, "unit": "us (p50)", "p99_us": p99,
-                      "higher_is_better": False, "n_gpus": 1, "chunks": len(lat),
-                      "audio_seconds_per_second_one_stream": 0.08 / (sum(lat) / len(lat) * 1e-6),
-                      "config": {"workload": "configs[3]: batch 1, 80 ms chunks (1280 samples), 16 kHz, 80 mel, 16 bins; "
-                                             "chunk already on the device, latency = push() + stream sync; 5 frames per chunk",
-                                 "note": "launch-latency bound: 5.5 KB per call, byte roofline not meaningful"}}))
+    return {"metric": "dmel_stream_chunk_latency_us", "value": p50, "unit": "us (p50)", "p99_us": p99,
+            "higher_is_better": False, "n_gpus": 1, "chunks": len(lat),
+            "audio_seconds_per_second_one_stream": 0.08 / (sum(lat) / len(lat) * 1e-6),
+            "config": {"workload": "configs[3]: batch 1, 80 ms chunks (1280 samples), 16 kHz, 80 mel, 16 bins; "
+                                   "chunk already on the device, latency = push() + stream sync; 5 frames per chunk",
+                       "note": "launch-latency bound: 5.5 KB per call, byte roofline not meaningful"}}
 
 
-def run_pool_workload(args, name):
-    """configs[2] (calibrate + encode of 10k utterances, sharded) and configs[4] (long-form 2048)."""
+def pool_workload(name, rank, world, dev):
+    """configs[2] (calibrate + encode of 10k utterances, sharded) and configs[4] (long-form 2048).  The timed
+    region is the whole job of this rank's shard including the statistics all-reduce (NCCL when world > 1);
+    max over ranks."""
     import torch.distributed as dist
     import dmel_codec_b200 as d
     from dmel_codec_b200 import distributed as D, synth
-    rank, world, local_rank, dev = _init_rank()
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29500")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     if name == "calibrate":
         geom = dict(sample_rate=16000, n_fft=1024, win_length=1024, hop_length=256, n_mels=80)
         n_utts, seconds, n_bins, bsz, pool_n = 10000, 10, 16, 250, 500
@@ -420,14 +551,16 @@ def run_pool_workload(args, name):
         label = "configs[4]: long-form 32 x 60 s, 44.1 kHz, n_fft 2048, hop 512, 160 mel, 32 bins, utterances sharded"
     n = geom["sample_rate"] * seconds
     tok = d.DMelTokenizer(n_bins=n_bins, **geom).to(dev)
-    mine = D.shard_range(n_utts, rank, world)
     # a pool of distinct synthetic utterances stands in for the shard (content does not change the work)
     pool = synth.device_batch(range(rank * pool_n, (rank + 1) * pool_n), n, geom["sample_rate"], dev)
+
     def load(ids):
         k = len(ids)
         start = (ids[0] * 7) % max(1, pool_n - k + 1) if k <= pool_n else 0
         return pool[start:start + k]
+
     two_pass = bool(os.environ.get("DMEL_BENCH_TWO_PASS"))
+
     def job():
         if two_pass:
             D.calibrate_sharded(tok, n_utts, load, bsz)            # pass 1 + the all-reduce
@@ -436,31 +569,88 @@ def run_pool_workload(args, name):
         else:  # pass 1 keeps the shard's log-mel in HBM, pass 2 is the stand-alone quantiser over it
             for _ in D.calibrate_encode_sharded(tok, n_utts, load, bsz):
                 pass
+
     job()
-    torch.cuda.synchronize()
+    times = []
+    for _ in range(5):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        job()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        times.append(ms.item())
+    ms_total = statistics.median(times)
+    audio_s = n_utts * seconds
+    t_frames = n // geom["hop_length"]
+    bytes_alg = 2 * 4 * n_utts * n + n_utts * geom["n_mels"] * t_frames  # two waveform reads + codes
+    bytes_job = 4 * n_utts * n + (4 + 4 + 1) * n_utts * geom["n_mels"] * t_frames  # what this job moves: wav, mel out, mel in, codes
+    peak, _ = measured_peaks()
+    out = {"metric": f"dmel_{name}_encode_audio_seconds_per_second", "value": audio_s / (ms_total / 1e3), "unit": UNIT,
+           "n_gpus": world, "ms_total": ms_total, "ms_runs": times, "higher_is_better": True, "scaling": "strong",
+           "hbm_frac_all_gpus": bytes_alg / (ms_total / 1e3) / 1e9 / (peak * world),
+           "hbm_frac_bytes_moved": bytes_job / (ms_total / 1e3) / 1e9 / (peak * world),
+           "collective": "all_reduce(MIN) of [lo, -hi] (2 * n_mels float32) inside the timed region" + ("" if world > 1 else " (no-op at 1 rank)"),
+           "stats": {"lo_min": float(tok.quantizer.lo.min()), "hi_max": float(tok.quantizer.hi.max())},
+           "config": {"workload": label, "launch": tok._plan(dev).describe(),
+                      "job": "two transform passes" if two_pass else
+                             "one transform pass (log-mel of the shard kept in HBM) + stand-alone quantiser pass",
+                      "data": f"pool of {pool_n} distinct synthetic utterances per rank, cycled; median of 5 runs"}}
+    del pool, tok
+    torch.cuda.empty_cache()
+    return out
+
+
+def standalone_kernels(dev):
+    """Roofline entries of the stand-alone quantiser stages at a size where HBM binds (1 GiB of log-mel: 8x the L2)."""
+    from dmel_codec_b200 import plan as P
+    b, m, t = 256, 128, 8192
+    mel = torch.empty((b, m, t), dtype=torch.float32, device=dev).uniform_(-11.5, 2.0)
+    lo = torch.full((m,), -11.6, dtype=torch.float32, device=dev)
+    hi = torch.full((m,), 2.1, dtype=torch.float32, device=dev)
+    scale, step = 16.0 / (hi - lo), (hi - lo) / 16.0
+    table = (lo[:, None] + (torch.arange(16, device=dev, dtype=torch.float32)[None, :] + 0.5) * step[:, None]).contiguous()
+    run_min = torch.full((m,), float("inf"), device=dev)
+    run_max = torch.full((m,), float("-inf"), device=dev)
+    stream = torch.cuda.current_stream(dev)
+    codes = P.quantize(mel, lo, scale, 16)
+    peak, _ = measured_peaks()
+    n = b * m * t
+    out = {}
+    for name, fn, nbytes in (
+            ("quantize_kernel", lambda i: P.quantize(mel, lo, scale, 16), 5 * n),
+            ("dequantize_kernel", lambda i: P.dequantize(codes, table), 5 * n),
+            ("tensor_minmax_kernel", lambda i: P.tensor_minmax(mel, None, run_min, run_max), 4 * n)):
+        for i in range(2):
+            fn(i)
+        ms = time_kernel_ms(fn, 7, stream)
+        out[name] = {"avg_launch_ms": ms, "algorithmic_bytes_per_launch": nbytes, "achieved": nbytes / (ms / 1e3) / 1e9,
+                     "unit": "GB/s", "frac": nbytes / (ms / 1e3) / 1e9 / peak, "shape": [b, m, t]}
+    del mel, codes
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_stream(args):
+    rank, world, local_rank, dev = _init_rank()
+    print(json.dumps(stream_workload(dev)))
+
+
+def run_pool_workload(args, name):
+    import torch.distributed as dist
+    rank, world, local_rank, dev = _init_rank()
     if world > 1:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    job()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.barrier()
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    out = pool_workload(name, rank, world, dev)
     if rank == 0:
-        audio_s = n_utts * seconds
-        bytes_alg = 2 * 4 * n_utts * n + n_utts * geom["n_mels"] * (n // geom["hop_length"])
-        peak, src = measured_peaks()
-        print(json.dumps({"metric": f"dmel_{name}_encode_audio_seconds_per_second", "value": audio_s / (ms.item() / 1e3),
-                          "unit": UNIT, "n_gpus": world, "ms_total": ms.item(), "higher_is_better": True,
-                          "scaling": "strong", "hbm_frac_all_gpus": bytes_alg / (ms.item() / 1e3) / 1e9 / (peak * world),
-                          "stats": {"lo_min": float(tok.quantizer.lo.min()), "hi_max": float(tok.quantizer.hi.max())},
-                          "config": {"workload": label, "launch": tok._plan(dev).describe(),
-                                     "job": "two transform passes" if two_pass else
-                                            "one transform pass (log-mel of the shard kept in HBM) + stand-alone quantiser pass",
-                                     "data": f"pool of {pool_n} distinct synthetic utterances per rank, cycled"}}))
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -475,7 +665,12 @@ def main():
                     help="encode = the headline configs[1] line; the others are secondary lines for DESIGN.md")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: leave out the CPU-baseline leg")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: leave out the host-buffer leg")
+    ap.add_argument("--skip-secondary", action="store_true", help="profiling runs: leave out configs[2..4] and the stand-alone kernels")
+    ap.add_argument("--skip-gpu-baseline", action="store_true", help="profiling runs: leave out the stock-torch GPU comparator")
+    ap.add_argument("--quick", action="store_true", help="headline region only (= all four --skip flags)")
     args = ap.parse_args()
+    if args.quick:
+        args.skip_cpu = args.skip_e2e = args.skip_secondary = args.skip_gpu_baseline = True
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -183,7 +183,10 @@ std::vector<int> deal_groups(const std::vector<int>& group_steps) {
   }
   std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return group_steps[a] > group_steps[b]; });
   std::vector<std::vector<int>> mine(kW);
-  int load[kW] = {kHandicap};
+  int load[kW] = {};
+  int book = 0;
+  if (const char* env = std::getenv("DMEL_BOOK_WARP")) book = std::atoi(env) & (kW - 1);  // measurements: which warp carries the bookkeeping thread
+  load[book] = kHandicap;
   for (int g : idx) {
     int w = 0;
     for (int k = 1; k < kW; ++k)
@@ -295,13 +298,26 @@ struct DeviceGuard {
   }
 };
 
-int stream_grid(const dmel_plan* /*unused*/, unsigned n_groups) {
-  int dev = 0, sms = 148;
+// The tensor-level entry points take no plan: the device is the one that owns the tensor.
+int device_of(const void* dev_ptr) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, dev_ptr) == cudaSuccess && attr.type == cudaMemoryTypeDevice) return attr.device;
+  cudaGetLastError();
+  int dev = 0;
   cudaGetDevice(&dev);
+  return dev;
+}
+
+int sm_count_of(int dev) {
+  int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+int stream_grid(int dev, unsigned n_groups) {
   const long long want = (n_groups + dmel::kStreamThreads * dmel::kStreamUnroll - 1LL) /
                          (dmel::kStreamThreads * dmel::kStreamUnroll);
-  return (int)std::max<long long>(1, std::min<long long>(want, 8LL * sms));
+  return (int)std::max<long long>(1, std::min<long long>(want, 8LL * sm_count_of(dev)));
 }
 
 }  // namespace
@@ -779,10 +795,8 @@ static int encode_host_impl(dmel_plan* plan, const void* wav_host_v, int elem, l
   DeviceGuard guard(plan->device);
   for (int i = 0; i < 2; ++i)
     if (!plan->streams[i]) DMEL_CUDA(cudaStreamCreateWithFlags(&plan->streams[i], cudaStreamNonBlocking));
-  if (!plan->d_lo) {
-    DMEL_CUDA(cudaMalloc((void**)&plan->d_lo, plan->n_mels * sizeof(float)));
-    DMEL_CUDA(cudaMalloc((void**)&plan->d_scale, plan->n_mels * sizeof(float)));
-  }
+  if (!plan->d_lo) DMEL_CUDA(cudaMalloc((void**)&plan->d_lo, plan->n_mels * sizeof(float)));
+  if (!plan->d_scale) DMEL_CUDA(cudaMalloc((void**)&plan->d_scale, plan->n_mels * sizeof(float)));
   // rows per chunk: at least four chunks per call so copies and kernels of neighbouring chunks overlap and the
   // un-overlapped tail (last kernel + last D2H) stays short, at most 16 MiB of waveform each (DMEL_HOST_CHUNK_MB pins it)
   const long long row_bytes = n_samples * elem;
@@ -823,8 +837,9 @@ static int encode_host_impl(dmel_plan* plan, const void* wav_host_v, int elem, l
   if (!plan->stats_ready) DMEL_CUDA(cudaEventCreateWithFlags(&plan->stats_ready, cudaEventDisableTiming));
   DMEL_CUDA(cudaEventRecord(plan->stats_ready, plan->streams[0]));
   DMEL_CUDA(cudaStreamWaitEvent(plan->streams[1], plan->stats_ready, 0));
-  int slot = 0;
-  for (long long r0 = 0; r0 < n_rows; r0 += chunk_rows, slot ^= 1) {
+  // From here on copies into the caller's host buffers may be in flight on both streams: every exit, error or
+  // not, goes through the two synchronisations below.
+  auto queue_chunk = [&](long long r0, int slot) -> int {
     const long long rows = std::min(chunk_rows, n_rows - r0);
     cudaStream_t st = plan->streams[slot];
     // stream order already guarantees the slot's previous D2H finished before this H2D starts
@@ -839,16 +854,27 @@ static int encode_host_impl(dmel_plan* plan, const void* wav_host_v, int elem, l
       DMEL_CUDA(cudaMemcpyAsync(plan->d_len[slot], lengths_host + r0, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
       len_dev = plan->d_len[slot];
     }
-    rc = elem == 2 ? dmel_encode_pcm16_u8(plan, reinterpret_cast<const int16_t*>(plan->d_wav[slot]), rows, n_samples, n_samples,
-                                          len_dev, plan->d_lo, plan->d_scale, n_bins, plan->d_codes[slot], st)
-                   : dmel_encode_u8(plan, plan->d_wav[slot], rows, n_samples, n_samples, len_dev, plan->d_lo, plan->d_scale,
-                                    n_bins, plan->d_codes[slot], nullptr, nullptr, 0.f, st);
-    if (rc != DMEL_OK) return rc;
+    const int rc_k = elem == 2 ? dmel_encode_pcm16_u8(plan, reinterpret_cast<const int16_t*>(plan->d_wav[slot]), rows, n_samples,
+                                                      n_samples, len_dev, plan->d_lo, plan->d_scale, n_bins, plan->d_codes[slot], st)
+                               : dmel_encode_u8(plan, plan->d_wav[slot], rows, n_samples, n_samples, len_dev, plan->d_lo,
+                                                plan->d_scale, n_bins, plan->d_codes[slot], nullptr, nullptr, 0.f, st);
+    if (rc_k != DMEL_OK) return rc_k;
     DMEL_CUDA(cudaMemcpyAsync(codes_host + (size_t)r0 * plan->n_mels * T, plan->d_codes[slot],
                               (size_t)rows * plan->n_mels * T, cudaMemcpyDeviceToHost, st));
+    return DMEL_OK;
+  };
+  int slot = 0;
+  rc = DMEL_OK;
+  for (long long r0 = 0; r0 < n_rows && rc == DMEL_OK; r0 += chunk_rows, slot ^= 1) rc = queue_chunk(r0, slot);
+  const std::string queued_error = rc == DMEL_OK ? std::string() : g_last_error;
+  const cudaError_t s0 = cudaStreamSynchronize(plan->streams[0]);
+  const cudaError_t s1 = cudaStreamSynchronize(plan->streams[1]);
+  if (rc != DMEL_OK) {
+    g_last_error = queued_error;
+    return rc;
   }
-  DMEL_CUDA(cudaStreamSynchronize(plan->streams[0]));
-  DMEL_CUDA(cudaStreamSynchronize(plan->streams[1]));
+  if (s0 != cudaSuccess || s1 != cudaSuccess)
+    return fail(DMEL_ERR_CUDA, "stream synchronisation failed: %s", cudaGetErrorString(s0 != cudaSuccess ? s0 : s1));
   return DMEL_OK;
 }
 
@@ -885,7 +911,9 @@ int dmel_quantize_u8(const float* logmel_dev, long long n_rows, int n_mels, long
   if (!lo_dev || !scale_dev) return fail(DMEL_ERR_INVALID, "lo_dev / scale_dev is null");
   if (n == 0) return DMEL_OK;
   const bool vec = ((reinterpret_cast<uintptr_t>(logmel_dev) & 15) == 0) && ((reinterpret_cast<uintptr_t>(codes_dev) & 3) == 0);
-  DMEL_CUDA(launch_pdl(dmel::quantize_kernel, dim3(stream_grid(nullptr, n >> 2)), dim3(dmel::kStreamThreads), 0, (cudaStream_t)stream,
+  const int dev = device_of(logmel_dev);
+  DeviceGuard guard(dev);
+  DMEL_CUDA(launch_pdl(dmel::quantize_kernel, dim3(stream_grid(dev, n >> 2)), dim3(dmel::kStreamThreads), 0, (cudaStream_t)stream,
                        logmel_dev, codes_dev, lo_dev, scale_dev, n, dmel::FastDiv::make((unsigned)n_frames),
                        dmel::FastDiv::make((unsigned)n_mels), (unsigned)n_bins, vec));
   return DMEL_OK;
@@ -900,7 +928,9 @@ int dmel_dequantize_f32(const uint8_t* codes_dev, long long n_rows, int n_mels, 
   if (!table_dev) return fail(DMEL_ERR_INVALID, "table_dev is null");
   if (n == 0) return DMEL_OK;
   const bool vec = ((reinterpret_cast<uintptr_t>(logmel_dev) & 15) == 0) && ((reinterpret_cast<uintptr_t>(codes_dev) & 3) == 0);
-  DMEL_CUDA(launch_pdl(dmel::dequantize_kernel, dim3(stream_grid(nullptr, n >> 2)), dim3(dmel::kStreamThreads), 0, (cudaStream_t)stream,
+  const int dev = device_of(codes_dev);
+  DeviceGuard guard(dev);
+  DMEL_CUDA(launch_pdl(dmel::dequantize_kernel, dim3(stream_grid(dev, n >> 2)), dim3(dmel::kStreamThreads), 0, (cudaStream_t)stream,
                        codes_dev, logmel_dev, table_dev, n, dmel::FastDiv::make((unsigned)n_frames),
                        dmel::FastDiv::make((unsigned)n_mels), (unsigned)n_bins, vec));
   return DMEL_OK;
@@ -914,7 +944,9 @@ int dmel_tensor_minmax_f32(const float* logmel_dev, long long n_rows, int n_mels
   if (!max_dev) return fail(DMEL_ERR_INVALID, "max_dev is null");
   if (n == 0) return DMEL_OK;
   const unsigned lines = (unsigned)(n_rows * n_mels);
-  const int blocks = (int)std::min<unsigned>((lines + 7) / 8, 148u * 8u);
+  const int dev = device_of(logmel_dev);
+  DeviceGuard guard(dev);
+  const int blocks = (int)std::min<unsigned>((lines + 7) / 8, (unsigned)sm_count_of(dev) * 8u);
   DMEL_CUDA(launch_pdl(dmel::tensor_minmax_kernel, dim3(blocks), dim3(dmel::kStreamThreads), 0, (cudaStream_t)stream,
                        logmel_dev, n_valid_dev, min_dev, max_dev, lines, (unsigned)n_frames, (unsigned)n_mels));
   return DMEL_OK;

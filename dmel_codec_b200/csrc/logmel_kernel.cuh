@@ -362,6 +362,11 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
   }
   const float2* my_win = reinterpret_cast<const float2*>(s_window) + lane;  // lean / 2048: taps re-read per frame
 
+#ifdef DMEL_BOOK_WARP
+  constexpr int kBook = DMEL_BOOK_WARP * 32;  // the thread that does the tile bookkeeping
+#else
+  constexpr int kBook = 0;
+#endif
   const bool hop_even = (p.hop & 1) == 0;
   unsigned long long edge_hits = 0;
   uint32_t wave_parity = 0;  // parity to wait for on the waveform barrier
@@ -464,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
   int tile = blockIdx.x;
   const TileInfo first = describe(tile < p.n_tiles ? tile : 0);
   if (tile < p.n_tiles) {
-    if (tid == 0) stage_bulk(first);  // the first tile leaves HBM while the statistics below are fetched
+    if (tid == kBook) stage_bulk(first);  // the first tile leaves HBM while the statistics below are fetched
     if (first.manual && first.frame_limit) stage_manual(first.row, first.t0, first.bulk_lo, first.bulk_n);
   }
   if constexpr (kCodes) {
@@ -491,7 +496,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
       wave_parity ^= 1u;
     }
     int fetched = 0;
-    if (dynamic && tid == 0) fetched = atomicAdd(p.sched, 1);  // consumed after the FFT barrier: its latency is never waited for
+    if (dynamic && tid == kBook) fetched = atomicAdd(p.sched, 1);  // consumed after the FFT barrier: its latency is never waited for
 
     // ---- 2. FFT -> magnitudes ------------------------------------------------
     const int fft_frames = DMEL_SKIP(p, 1) ? 0 : cur_limit;
@@ -619,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
     __syncthreads();  // magnitudes complete, the wave buffer is free
     // One thread finds out which tile comes next, describes it and starts its copy, which flies under the mel
     // phase; that thread's warp carries the lightest share of the mel phase to make up for it.
-    if (tid == 0) {
+    if (tid == kBook) {
       const int next_tile = dynamic ? (int)gridDim.x + fetched : tile + (int)gridDim.x;
       TileInfo nd = first;
       if (next_tile < p.n_tiles) {

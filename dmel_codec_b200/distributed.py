@@ -71,12 +71,18 @@ def calibrate_encode_sharded(tokenizer, n_utterances: int, load_batch: Callable[
     statistics are all-reduced, and pass 2 is the stand-alone quantiser over the stored log-mel —
     an HBM-bound pass of 5 bytes per value instead of a second transform.  Same codes, bit for bit, as
     the two-pass job (the fused encode quantises exactly these float32 values).  Needs 4 bytes per
-    log-mel value of the shard in HBM (2 GB for 10,000 x 10 s at 80 mel); fall back to the two-pass
-    functions when the shard does not fit."""
+    log-mel value of the shard in HBM (2 GB for 10,000 x 10 s at 80 mel); when that is more than
+    ``KEEP_MEL_HBM_FRACTION`` of the free HBM the job runs as the two transform passes instead."""
     rank, size = world()
+    mine = shard_range(n_utterances, rank, size)
+    if not _shard_logmel_fits(tokenizer, mine, load_batch, batch_size):
+        # the shard's log-mel does not fit next to the waveforms: two transform passes instead, same codes
+        calibrate_sharded(tokenizer, n_utterances, load_batch, batch_size, group=group)
+        yield from encode_sharded(tokenizer, n_utterances, load_batch, batch_size)
+        return
     tokenizer.quantizer.reset_stats()
     kept = []
-    for ids in batches(shard_range(n_utterances, rank, size), batch_size):
+    for ids in batches(mine, batch_size):
         item = load_batch(ids)
         audios, lengths = item if isinstance(item, (tuple, list)) else (item, None)
         kept.append((ids, tokenizer.update_stats_keep_mel(audios, lengths), lengths))
@@ -90,3 +96,26 @@ def calibrate_encode_sharded(tokenizer, n_utterances: int, load_batch: Callable[
             codes = codes * (t[None, None, :] < code_lengths[:, None, None])  # the fused encode writes 0 past the valid frames
         yield ids, codes, code_lengths
 
+
+# fraction of the free HBM the stored log-mel of a shard may take (the rest: waveform batches, codes, allocator slack)
+KEEP_MEL_HBM_FRACTION = 0.6
+
+
+def _shard_logmel_fits(tokenizer, ids: Sequence[int], load_batch, batch_size: int) -> bool:
+    """Whether 4 bytes per log-mel value of this rank's shard fit in free HBM.  The size is estimated from the
+    first batch (utterances of a shard are of similar length by construction of a bucketing sampler, reference
+    dataset/lhotse_tts_dataset.py:184-191); DMEL_KEEP_MEL=0/1 overrides the decision."""
+    import os
+    forced = os.environ.get("DMEL_KEEP_MEL")
+    if forced is not None:
+        return forced != "0"
+    if len(ids) == 0:
+        return True
+    item = load_batch(ids[:batch_size])
+    audios = item[0] if isinstance(item, (tuple, list)) else item
+    if not audios.is_cuda:
+        return True
+    frames = audios.shape[-1] // tokenizer.hop_length
+    need = 4 * len(ids) * tokenizer.quantizer.n_mels * frames
+    free, _total = torch.cuda.mem_get_info(audios.device)
+    return need <= KEEP_MEL_HBM_FRACTION * free

@@ -25,6 +25,17 @@ def _stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def _require_stat(t: torch.Tensor, what: str, device: torch.device, n: int) -> None:
+    """Per-channel statistics and tables go to the kernels as raw float32 pointers: a tensor on another device,
+    of another dtype or too short would be read as garbage (or fault the context), so check before the call."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device != device:
+        raise ValueError(f"{what} must be a CUDA tensor on {device} (the audio's device); got "
+                         f"{getattr(t, 'device', type(t))}. Move the module with .to(device) first")
+    if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < n:
+        raise ValueError(f"{what} must be a contiguous float32 tensor of at least {n} elements, "
+                         f"got {t.dtype} {tuple(t.shape)} (contiguous={t.is_contiguous()})")
+
+
 def as_rows(wav: torch.Tensor) -> torch.Tensor:
     """(B, L) or (B, 1, L) -> (B, L) float32 with unit stride along L, the two
     input layouts the reference accepts (utils/spectrogram.py:60-62)."""
@@ -120,6 +131,8 @@ class Plan:
         rows = as_rows(wav)
         b, n = rows.shape
         t = self._frames_or_raise(n)
+        if row_sum is not None:
+            _require_stat(row_sum, "row_sum", rows.device, b * self.n_mels)
         out = torch.empty((b, self.n_mels, t), dtype=dtype, device=rows.device)
         len_ptr = self._lengths_ptr(lengths, b, rows.device)
         _native.check(_native.load().dmel_logmel_masked(
@@ -135,6 +148,8 @@ class Plan:
         rows = as_rows(wav)
         b, n = rows.shape
         self._frames_or_raise(n)
+        _require_stat(run_min, "run_min", rows.device, self.n_mels)
+        _require_stat(run_max, "run_max", rows.device, self.n_mels)
         len_ptr = self._lengths_ptr(lengths, b, rows.device)
         _native.check(_native.load().dmel_minmax_f32(
             self._handle, rows.data_ptr(), b, n, rows.stride(0) if b > 1 else n, len_ptr[0],
@@ -147,6 +162,8 @@ class Plan:
         rows = as_rows(wav)
         b, n = rows.shape
         t = self._frames_or_raise(n)
+        _require_stat(run_min, "run_min", rows.device, self.n_mels)
+        _require_stat(run_max, "run_max", rows.device, self.n_mels)
         out = torch.empty((b, self.n_mels, t), dtype=torch.float32, device=rows.device)
         len_ptr = self._lengths_ptr(lengths, b, rows.device)
         _native.check(_native.load().dmel_logmel_minmax_f32(
@@ -162,6 +179,8 @@ class Plan:
         rows = as_rows(wav)
         b, n = rows.shape
         t = self._frames_or_raise(n)
+        _require_stat(lo, "lo", rows.device, self.n_mels)
+        _require_stat(scale, "scale", rows.device, self.n_mels)
         codes = torch.empty((b, self.n_mels, t), dtype=torch.uint8, device=rows.device)
         logmel = torch.empty((b, self.n_mels, t), dtype=torch.float32, device=rows.device) if return_logmel else None
         len_ptr = self._lengths_ptr(lengths, b, rows.device)
@@ -180,6 +199,8 @@ class Plan:
         rows = as_rows(wav)
         b, n = rows.shape
         t = self._frames_or_raise(n)
+        for name, stat in (("lo", lo), ("scale", scale), ("step", step)):
+            _require_stat(stat, name, rows.device, self.n_mels)
         codes = torch.empty((b, self.n_mels, t), dtype=torch.uint8, device=rows.device)
         mel_hat = torch.empty((b, self.n_mels, t), dtype=torch.float32, device=rows.device)
         len_ptr = self._lengths_ptr(lengths, b, rows.device)
@@ -196,6 +217,8 @@ class Plan:
         rows = as_pcm_rows(wav)
         b, n = rows.shape
         t = self._frames_or_raise(n)
+        _require_stat(lo, "lo", rows.device, self.n_mels)
+        _require_stat(scale, "scale", rows.device, self.n_mels)
         codes = torch.empty((b, self.n_mels, t), dtype=torch.uint8, device=rows.device)
         len_ptr = self._lengths_ptr(lengths, b, rows.device)
         _native.check(_native.load().dmel_encode_pcm16_u8(
@@ -215,6 +238,10 @@ class Plan:
         t = self._frames_or_raise(n)
         if out is None:
             out = torch.empty((b, self.n_mels, t), dtype=torch.uint8, pin_memory=True)
+        elif (out.is_cuda or out.dtype != torch.uint8 or tuple(out.shape) != (b, self.n_mels, t)
+              or not out.is_contiguous()):
+            raise ValueError(f"out must be a contiguous CPU uint8 tensor of shape {(b, self.n_mels, t)}, got "
+                             f"{out.dtype} {tuple(out.shape)} on {out.device}")
         lo_h = lo.detach().to("cpu", torch.float32).contiguous()
         sc_h = scale.detach().to("cpu", torch.float32).contiguous()
         len_h = None
@@ -248,9 +275,12 @@ class Plan:
         flat = lengths.reshape(-1)
         if flat.numel() != b:
             raise ValueError(f"lengths has {flat.numel()} entries for a batch of {b}")
-        flat = flat.to(device=device, dtype=torch.int32).contiguous()
-        self._len_keepalive = flat  # stays alive until the next call on this plan
-        return flat.data_ptr(), flat
+        converted = flat.to(device=device, dtype=torch.int32).contiguous()
+        if converted.data_ptr() != flat.data_ptr() or converted.dtype != flat.dtype:
+            # a temporary of ours: the launch is asynchronous, so tell the caching allocator that the launching
+            # stream still reads it (two launches of one plan on two streams each keep their own lengths alive)
+            converted.record_stream(torch.cuda.current_stream(device))
+        return converted.data_ptr(), converted
 
 
 # ---------------------------------------------------------------------------
@@ -262,6 +292,8 @@ def quantize(mel: torch.Tensor, lo: torch.Tensor, scale: torch.Tensor, n_bins: i
         raise ValueError(f"expected (B, n_mels, T), got {tuple(mel.shape)}")
     x = mel.float().contiguous()
     b, m, t = x.shape
+    _require_stat(lo, "lo", x.device, m)
+    _require_stat(scale, "scale", x.device, m)
     codes = torch.empty((b, m, t), dtype=torch.uint8, device=x.device)
     if x.numel():
         _native.check(_native.load().dmel_quantize_u8(
@@ -276,8 +308,9 @@ def dequantize(codes: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
         raise ValueError(f"expected uint8 codes (B, n_mels, T), got {codes.dtype} {tuple(codes.shape)}")
     c = codes.contiguous()
     b, m, t = c.shape
-    if table.shape[0] != m:
-        raise ValueError(f"codes have {m} channels, the quantiser has {table.shape[0]}")
+    if table.ndim != 2 or table.shape[0] != m:
+        raise ValueError(f"codes have {m} channels, the quantiser table is {tuple(table.shape)}")
+    _require_stat(table, "table", c.device, table.numel())
     out = torch.empty((b, m, t), dtype=torch.float32, device=c.device)
     if c.numel():
         _native.check(_native.load().dmel_dequantize_f32(
@@ -291,6 +324,8 @@ def tensor_minmax(mel: torch.Tensor, n_valid: Optional[torch.Tensor], run_min: t
     _require_cuda(mel, "mel")
     x = mel.float().contiguous()
     b, m, t = x.shape
+    _require_stat(run_min, "run_min", x.device, m)
+    _require_stat(run_max, "run_max", x.device, m)
     nv = None
     if n_valid is not None:
         nv = n_valid.reshape(-1).to(device=x.device, dtype=torch.int32).contiguous()

@@ -57,7 +57,13 @@ class DMelQuantizer(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() move the buffers
         self._invalidate()
-        return super()._apply(fn, *args, **kwargs)
+        out = super()._apply(fn, *args, **kwargs)
+        # .half() / .bfloat16() / .double() on a parent module would cast the statistics too; the kernels read them
+        # as float32 and the bin edges are defined in float32, so only the device follows such a call
+        if self.lo.dtype != torch.float32:
+            self.lo = self.lo.to(torch.float32)
+            self.hi = self.hi.to(torch.float32)
+        return out
 
     def _load_from_state_dict(self, *args, **kwargs):
         self._invalidate()
@@ -91,13 +97,16 @@ class DMelQuantizer(nn.Module):
     @torch.no_grad()
     def sync_stats(self, group=None) -> None:
         """All-reduce lo (MIN) and hi (MAX) across ranks: the one collective of
-        the whole path (2 * n_mels floats, NCCL over NVLink when on GPUs)."""
+        the whole path (one message of 2 * n_mels floats, NCCL over NVLink when on GPUs)."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()):
             return
         self._invalidate()
-        dist.all_reduce(self.lo, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(self.hi, op=dist.ReduceOp.MAX, group=group)
+        # one collective: MIN over [lo, -hi] (negation is exact, so max(hi) = -min(-hi) bit for bit; SURVEY.md 8e)
+        both = torch.cat([self.lo, -self.hi])
+        dist.all_reduce(both, op=dist.ReduceOp.MIN, group=group)
+        self.lo.copy_(both[: self.n_mels])
+        self.hi.copy_(-both[self.n_mels:])
 
     def scale(self) -> Tensor:
         """K / (hi - lo) per channel, 0 where the channel is degenerate."""

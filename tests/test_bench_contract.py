@@ -1,5 +1,6 @@
-"""bench.py contract checks that need no GPU: the reference arm runs the CPU oracle port and prints
-one JSON line with the agreed keys; the headline constants match BASELINE.json configs[1]."""
+"""bench.py contract checks that need no GPU: the reference arm runs the reference's own file from baseline/_ref
+(the oracle port where that is absent) and prints one JSON line with the agreed keys; both arms carry the same
+`config`; the headline constants match BASELINE.json configs[1]."""
 import json
 import os
 import subprocess
@@ -19,7 +20,12 @@ def test_reference_arm_prints_the_contract_line():
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in line, key
     assert line["metric"] == "dmel_encode_audio_seconds_per_second" and line["unit"] == "audio-s/s"
-    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from baseline import ref_arm
+    assert line["value"] > 0 and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_arm.available() else "port")
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.config_block()  # the key-for-key config our own arm prints
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
 
 
