@@ -14,8 +14,22 @@ from ctypes import (POINTER, c_char_p, c_float, c_int, c_int32, c_longlong, c_ui
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DMEL_LIB") or os.path.join(_HERE, "libdmel_b200.so")  # DMEL_LIB: A/B builds
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = -1, -2, -3, -4
+
+class DmelIO(ctypes.Structure):
+    """``dmel_io`` of include/dmel_b200.h, field for field."""
+    _fields_ = [
+        ("struct_size", ctypes.c_size_t),
+        ("wav_dev", c_void_p), ("wav_is_pcm16", c_int),
+        ("n_rows", c_longlong), ("n_samples", c_longlong), ("row_stride", c_longlong),
+        ("offsets_dev", c_void_p), ("lengths_dev", c_void_p), ("own_length", c_int), ("min_row_samples", c_longlong),
+        ("row_gain_dev", c_void_p),
+        ("lo_dev", c_void_p), ("scale_dev", c_void_p), ("step_dev", c_void_p), ("n_bins", c_int),
+        ("codes_dev", c_void_p), ("mel_hat_dev", c_void_p), ("logmel_dev", c_void_p), ("logmel_is_bf16", c_int),
+        ("mask_invalid", c_int), ("min_dev", c_void_p), ("max_dev", c_void_p),
+    ]
+
 
 # name -> (restype, argtypes); mirrors include/dmel_b200.h one to one
 SIGNATURES = {
@@ -53,6 +67,9 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_int, c_void_p]),
     "dmel_encode_host_pcm16_u8": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_void_p,
                                           c_void_p, c_void_p, c_int, c_void_p]),
+    "dmel_run": (c_int, [c_void_p, POINTER(DmelIO), c_void_p]),
+    "dmel_row_peak_gain_f32": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong, c_void_p, c_void_p, c_float,
+                                       c_void_p, c_void_p]),
     "dmel_quantize_u8": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p]),
     "dmel_dequantize_f32": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_int, c_void_p,

@@ -20,6 +20,7 @@
 #include "launch_util.cuh"
 #include "logmel_kernel.cuh"
 #include "codec_kernels.cuh"
+#include "extras_kernels.cuh"
 
 namespace {
 
@@ -632,6 +633,85 @@ int dmel_encode_frames_u8(dmel_plan* plan, const float* wav_dev, long long n_row
   p.logmel = logmel_dev;
   DeviceGuard guard(plan->device);
   DMEL_CUDA(launch_fused_any(plan, p, grid, (cudaStream_t)stream));
+  return DMEL_OK;
+}
+
+int dmel_run(dmel_plan* plan, const dmel_io* io, void* stream) {
+  if (!io) return fail(DMEL_ERR_INVALID, "io is null");
+  if (io->struct_size != sizeof(dmel_io))
+    return fail(DMEL_ERR_INVALID, "dmel_io is %zu bytes in this library, the caller passed %zu", sizeof(dmel_io), io->struct_size);
+  FusedParams p;
+  int grid = 0;
+  const bool ragged = io->offsets_dev != nullptr;
+  const bool own = ragged || io->own_length != 0;
+  const long long stride = ragged ? io->n_samples : io->row_stride;
+  int rc = prepare_window(plan, static_cast<const float*>(io->wav_dev), io->n_rows, io->n_samples, stride, 0, 0, -1, &p, &grid);
+  if (rc != DMEL_OK) return rc;
+  if (own) {
+    if (!ragged && !io->lengths_dev) return fail(DMEL_ERR_INVALID, "own_length needs lengths_dev (or the ragged layout)");
+    if (io->min_row_samples <= plan->pad_inner)
+      return fail(DMEL_ERR_INVALID, "reflect padding of %d needs more than %d samples per utterance, the shortest has %lld "
+                  "(the reference's F.pad raises here too)", plan->pad_inner, plan->pad_inner, io->min_row_samples);
+    if (plan->pad_outer) return fail(DMEL_ERR_UNSUPPORTED, "own-length rows with center=True are not supported");
+  }
+  const bool want_codes = io->codes_dev != nullptr, want_stats = io->min_dev != nullptr || io->max_dev != nullptr;
+  if (!want_codes && !io->logmel_dev && !want_stats) return fail(DMEL_ERR_INVALID, "no output requested");
+  if (want_codes && want_stats) return fail(DMEL_ERR_INVALID, "codes and statistics cannot be produced by one call");
+  if (want_stats && (!io->min_dev || !io->max_dev)) return fail(DMEL_ERR_INVALID, "min_dev / max_dev is null");
+  if (io->mel_hat_dev && !want_codes) return fail(DMEL_ERR_INVALID, "mel_hat_dev needs codes_dev");
+  if (want_codes) {
+    if ((rc = check_bins(io->n_bins)) != DMEL_OK) return rc;
+    if (!io->lo_dev || !io->scale_dev || (io->mel_hat_dev && !io->step_dev))
+      return fail(DMEL_ERR_INVALID, "lo_dev / scale_dev / step_dev is null");
+  }
+  if (io->wav_is_pcm16) {
+    if (!plan->variant->lean) return fail(DMEL_ERR_UNSUPPORTED, "int16 input needs the register-lean kernel variant, which does not fit this geometry");
+    if (io->row_gain_dev) return fail(DMEL_ERR_UNSUPPORTED, "row_gain_dev applies to float32 waveforms only");
+    if (!(want_codes && !io->mel_hat_dev && !io->logmel_dev)) return fail(DMEL_ERR_UNSUPPORTED, "int16 input is built for the code output only");
+    p.window = plan->d_window_pcm;
+  }
+  if (io->n_rows == 0) return DMEL_OK;
+  p.offsets = io->offsets_dev;
+  p.own_length = own ? 1 : 0;
+  p.lengths = io->lengths_dev;
+  p.row_gain = io->row_gain_dev;
+  p.logmel = static_cast<float*>(io->logmel_dev);
+  p.mask_invalid = (io->mask_invalid || own) && (io->lengths_dev != nullptr || own);
+  p.run_min = io->min_dev;
+  p.run_max = io->max_dev;
+  if (want_codes) {
+    p.q_lo = io->lo_dev;
+    p.q_scale = io->scale_dev;
+    p.q_step = io->step_dev;
+    p.n_bins = io->n_bins;
+    p.kmax = float(io->n_bins - 1);
+    p.codes = io->codes_dev;
+    p.dequant = io->mel_hat_dev;
+  }
+  DeviceGuard guard(plan->device);
+  const cudaError_t e = launch_fused_any(plan, p, grid, (cudaStream_t)stream, io->logmel_is_bf16 != 0, io->wav_is_pcm16 != 0);
+  if (e == cudaErrorInvalidValue) return fail(DMEL_ERR_UNSUPPORTED, "this combination of outputs is not built (see logmel_kernel.cuh MODE list)");
+  DMEL_CUDA(e);
+  return DMEL_OK;
+}
+
+int dmel_row_peak_gain_f32(const float* wav_dev, long long n_rows, long long n_samples, long long row_stride,
+                           const long long* offsets_dev, const int32_t* lengths_dev, float target_peak,
+                           float* gain_dev, void* stream) {
+  if (!wav_dev || !gain_dev) return fail(DMEL_ERR_INVALID, "wav_dev / gain_dev is null");
+  if (n_rows < 0 || n_samples <= 0 || n_samples > (1LL << 30) || (!offsets_dev && row_stride < n_samples))
+    return fail(DMEL_ERR_INVALID, "bad waveform shape: rows=%lld samples=%lld stride=%lld", n_rows, n_samples, row_stride);
+  if (n_rows > 65535) return fail(DMEL_ERR_INVALID, "at most 65535 rows per call, got %lld", n_rows);
+  if (n_rows == 0) return DMEL_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  DeviceGuard guard(device_of(wav_dev));
+  // the gains double as the scratch for the running maxima (bit patterns of |x|)
+  DMEL_CUDA(cudaMemsetAsync(gain_dev, 0, (size_t)n_rows * sizeof(float), st));
+  const dim3 grid((unsigned)((n_samples + dmel::kAbsmaxChunk - 1) / dmel::kAbsmaxChunk), (unsigned)n_rows);
+  DMEL_CUDA(launch_pdl(dmel::row_absmax_kernel, grid, dim3(dmel::kAbsmaxThreads), 0, st, wav_dev, offsets_dev, lengths_dev,
+                       row_stride, (int)n_samples, reinterpret_cast<unsigned*>(gain_dev)));
+  DMEL_CUDA(launch_pdl(dmel::row_gain_kernel, dim3((unsigned)((n_rows + 127) / 128)), dim3(128), 0, st,
+                       reinterpret_cast<const unsigned*>(gain_dev), target_peak, gain_dev, (int)n_rows));
   return DMEL_OK;
 }
 

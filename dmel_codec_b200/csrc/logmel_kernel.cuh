@@ -90,6 +90,12 @@ struct FusedParams {
   const int* group_order;   // (n_order) channel group of warp w in its r-th trip at [r * warps + w], -1 = none: balances the mel phase
   const float* weights;
   const int* lengths;       // valid samples per row, or null
+  // ---- input-side options (reference dataset/lhotse_tts_dataset.py:29-33 and :46-65 do these on the host) ----
+  const long long* offsets; // ragged batch: row b is wav[offsets[b], offsets[b + 1]) (n_rows + 1 entries; only its first lengths[b]
+                            // samples when lengths is given too), row_stride unused; or null
+  int own_length;           // 1: every row is an utterance of its own length (lengths[b], or the offsets' difference):
+                            //    the reflect padding refers to THAT length, as if the reference ran on the row alone
+  const float* row_gain;    // (B) gain applied to the samples of a row (per-utterance peak normalisation), or null; float32 input only
   float* logmel;            // (B, M, T)            [kOutLogmel]; __nv_bfloat16 with kOutBf16
   int mask_invalid;         // log-mel of frames at or past lengths[b] / hop is written as 0 (the caller's mel * mask)
   float* row_sum;           // (B, M) or null: += sum over the frames of each row and channel of the log-mel as written [kOutLogmel]
@@ -386,19 +392,37 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
     // log-mel output covers every frame of the row (unless masked); codes / statistics only the valid ones
     const int last = ((kLogmel && !p.mask_invalid) ? p.n_frames : ti.n_valid) - ti.t0;
     ti.frame_limit = last < 0 ? 0 : (last > TF ? TF : last);
+    // the row as the reflect padding sees it: n samples starting at flat offset base (ragged batches, own-length rows)
+    int n = p.n_samples;
+    long long base = (long long)ti.row * p.row_stride;
+    if (p.offsets) {
+      base = p.offsets[ti.row];
+      n = (int)(p.offsets[ti.row + 1] - base);
+      if (p.lengths) n = min(n, max(p.lengths[ti.row], 0));  // rows may be stored with alignment slack between them
+    } else if (p.own_length) {
+      n = p.lengths[ti.row];
+    }
+    if (p.own_length) {
+      const int nv = (n <= 0 ? 0 : (int)p.by_hop.div((unsigned)n)) - p.t_begin;  // an utterance has n / hop frames
+      const int cap = ti.n_valid;
+      ti.n_valid = nv < 0 ? 0 : (nv < cap ? nv : cap);
+      const int last_own = ti.n_valid - ti.t0;  // nothing past the utterance's own frames is computed
+      ti.frame_limit = last_own < 0 ? 0 : (last_own > TF ? TF : last_own);
+    }
     const int s0 = (p.t_begin + ti.t0) * p.hop - p.pad_inner - p.pad_outer;  // virtual sample under the tile's first tap
     const int b0 = s0 - p.src_base;                                          // where that sample sits in the buffer
-    ti.src0 = (long long)ti.row * p.row_stride + b0;
+    ti.src0 = base + b0;
     constexpr int kA = kAlign - 1;
-    if (p.bulk_ok && s0 >= 0 && b0 >= 0 && (b0 & kA) == 0 && s0 + p.wave_len <= p.n_samples) {
+    const bool base_ok = p.bulk_ok && (!p.offsets || (base & kA) == 0);
+    if (base_ok && s0 >= 0 && b0 >= 0 && (b0 & kA) == 0 && s0 + p.wave_len <= n) {
       ti.bulk_lo = 0;  // interior tile (all but one or two per row): one copy brings everything
       ti.bulk_n = p.wave_len;
       ti.manual = 0;
     } else {
       int lo = s0 < 0 ? ((-s0 + kA) & ~kA) : 0;                                 // first wave index with a real sample
       if (b0 + lo < 0) lo = (-b0 + kA) & ~kA;                                   // ... that is resident in the buffer
-      int hi = p.n_samples - s0 < p.wave_len ? ((p.n_samples - s0) & ~kA) : p.wave_len;  // one past the last
-      const bool can_bulk = p.bulk_ok && (b0 & kA) == 0 && hi > lo;
+      int hi = n - s0 < p.wave_len ? ((n - s0) & ~kA) : p.wave_len;             // one past the last
+      const bool can_bulk = base_ok && (b0 & kA) == 0 && hi > lo;
       ti.bulk_lo = can_bulk ? lo : 0;
       ti.bulk_n = can_bulk ? hi - lo : 0;
       ti.manual = (!can_bulk || lo > 0 || hi < p.wave_len) ? 1 : 0;
@@ -423,15 +447,24 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
   auto stage_manual = [&](int row, int t0, int bulk_lo, int bulk_n) {
     if (DMEL_SKIP(p, 4)) return;
     wave_t* wave = wave0;
-    const int padded_len = p.n_samples + 2 * p.pad_inner + 2 * p.pad_outer;
-    const wave_t* src = wav + (long long)row * p.row_stride - p.src_base;
+    int n = p.n_samples;
+    long long base = (long long)row * p.row_stride;
+    if (p.offsets) {
+      base = p.offsets[row];
+      n = (int)(p.offsets[row + 1] - base);
+      if (p.lengths) n = min(n, max(p.lengths[row], 0));
+    } else if (p.own_length) {
+      n = p.lengths[row];
+    }
+    const int padded_len = n + 2 * p.pad_inner + 2 * p.pad_outer;
+    const wave_t* src = wav + base - p.src_base;
     const int j0 = (p.t_begin + t0) * p.hop;  // first position in the padded row
     const int n_manual = p.wave_len - bulk_n;
     for (int q = tid; q < n_manual; q += kThreads) {
       const int i = q < bulk_lo ? q : q + bulk_n;  // wave index outside the bulk range
       const int j = j0 + i;
       wave_t x = 0;
-      if (j < padded_len) x = __ldg(src + reflect_src(j, p.n_samples, p.pad_inner, p.pad_outer));
+      if (j < padded_len) x = __ldg(src + reflect_src(j, n, p.pad_inner, p.pad_outer));
       wave[i] = x;
     }
   };
@@ -497,6 +530,18 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
     }
     int fetched = 0;
     if (dynamic && tid == kBook) fetched = atomicAdd(p.sched, 1);  // consumed after the FFT barrier: its latency is never waited for
+    if constexpr (!kPcm) {
+      if (p.row_gain != nullptr && !dead) {  // per-utterance gain (peak normalisation): scale the staged tile in place
+        const float gain = __ldg(p.row_gain + cur_row);
+        float4* w4 = reinterpret_cast<float4*>(wave0);
+        for (int i = tid; i < p.wave_len / 4; i += kThreads) {
+          float4 x = w4[i];
+          x.x *= gain, x.y *= gain, x.z *= gain, x.w *= gain;
+          w4[i] = x;
+        }
+        __syncthreads();
+      }
+    }
 
     // ---- 2. FFT -> magnitudes ------------------------------------------------
     const int fft_frames = DMEL_SKIP(p, 1) ? 0 : cur_limit;

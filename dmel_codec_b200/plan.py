@@ -257,6 +257,100 @@ class Plan:
                 int(n_bins), out.data_ptr()))
         return out
 
+    # -- the general call: every input layout, every output ---------------------
+    def run(self, wav: torch.Tensor, *, lengths: Optional[torch.Tensor] = None, offsets: Optional[torch.Tensor] = None,
+            n_rows: Optional[int] = None, max_samples: Optional[int] = None, min_samples: Optional[int] = None,
+            own_length: bool = False, row_gain: Optional[torch.Tensor] = None,
+            lo: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None, step: Optional[torch.Tensor] = None,
+            n_bins: int = 0, want_codes: bool = False, want_mel_hat: bool = False, want_logmel: bool = False,
+            logmel_dtype: torch.dtype = torch.float32, mask_invalid: bool = False,
+            run_min: Optional[torch.Tensor] = None, run_max: Optional[torch.Tensor] = None) -> dict:
+        """``dmel_run``: padded ``wav`` (B, L) / (B, 1, L), or a flat ragged buffer with ``offsets`` (B + 1 int64,
+        CUDA; then ``n_rows``, ``max_samples`` and ``min_samples`` describe the rows).  Returns the requested
+        outputs by name: ``codes``, ``mel_hat``, ``logmel``."""
+        _require_cuda(wav, "audio")
+        pcm = wav.dtype == torch.int16
+        dev = wav.device
+        if offsets is not None:
+            flat = wav.reshape(-1)
+            if flat.stride(0) != 1:
+                flat = flat.contiguous()
+            if not pcm and flat.dtype != torch.float32:
+                flat = flat.float()
+            if n_rows is None or max_samples is None or min_samples is None:
+                raise ValueError("a ragged batch needs n_rows, max_samples and min_samples (host-side numbers)")
+            off = offsets.to(device=dev, dtype=torch.int64).contiguous()
+            if off.numel() != n_rows + 1:
+                raise ValueError(f"offsets has {off.numel()} entries for {n_rows} rows")
+            if off.data_ptr() != offsets.data_ptr():
+                off.record_stream(torch.cuda.current_stream(dev))
+            rows, b, n, stride = flat, int(n_rows), int(max_samples), int(max_samples)
+        else:
+            rows = as_pcm_rows(wav) if pcm else as_rows(wav)
+            b, n = rows.shape
+            stride = rows.stride(0) if b > 1 else n
+            off = None
+            if own_length and min_samples is None:
+                raise ValueError("own_length needs min_samples: the shortest utterance, known on the host")
+        t = self._frames_or_raise(n)
+        io = _native.DmelIO()
+        io.struct_size = ctypes.sizeof(_native.DmelIO)
+        io.wav_dev, io.wav_is_pcm16 = rows.data_ptr(), int(pcm)
+        io.n_rows, io.n_samples, io.row_stride = b, n, stride
+        io.offsets_dev = off.data_ptr() if off is not None else None
+        len_ptr, _keep = self._lengths_ptr(lengths, b, dev)
+        io.lengths_dev = len_ptr
+        io.own_length = int(bool(own_length) or off is not None)
+        io.min_row_samples = int(min_samples) if min_samples is not None else n
+        if row_gain is not None:
+            _require_stat(row_gain, "row_gain", dev, b)
+            io.row_gain_dev = row_gain.data_ptr()
+        out = {}
+        if want_codes:
+            _require_stat(lo, "lo", dev, self.n_mels)
+            _require_stat(scale, "scale", dev, self.n_mels)
+            io.lo_dev, io.scale_dev, io.n_bins = lo.data_ptr(), scale.data_ptr(), int(n_bins)
+            out["codes"] = torch.empty((b, self.n_mels, t), dtype=torch.uint8, device=dev)
+            io.codes_dev = out["codes"].data_ptr()
+            if want_mel_hat:
+                _require_stat(step, "step", dev, self.n_mels)
+                io.step_dev = step.data_ptr()
+                out["mel_hat"] = torch.empty((b, self.n_mels, t), dtype=torch.float32, device=dev)
+                io.mel_hat_dev = out["mel_hat"].data_ptr()
+        if want_logmel:
+            if logmel_dtype not in (torch.float32, torch.bfloat16):
+                raise ValueError(f"logmel_dtype must be torch.float32 or torch.bfloat16, got {logmel_dtype}")
+            out["logmel"] = torch.empty((b, self.n_mels, t), dtype=logmel_dtype, device=dev)
+            io.logmel_dev, io.logmel_is_bf16 = out["logmel"].data_ptr(), int(logmel_dtype == torch.bfloat16)
+        io.mask_invalid = int(mask_invalid)
+        if run_min is not None or run_max is not None:
+            _require_stat(run_min, "run_min", dev, self.n_mels)
+            _require_stat(run_max, "run_max", dev, self.n_mels)
+            io.min_dev, io.max_dev = run_min.data_ptr(), run_max.data_ptr()
+        _native.check(_native.load().dmel_run(self._handle, ctypes.byref(io), _stream_ptr(dev)))
+        return out
+
+    def peak_gain(self, wav: torch.Tensor, *, lengths: Optional[torch.Tensor] = None, offsets: Optional[torch.Tensor] = None,
+                  n_rows: Optional[int] = None, max_samples: Optional[int] = None, target: float = 0.95) -> torch.Tensor:
+        """(B,) float32 gains ``target / max|x|`` over the valid samples of every row (``dmel_row_peak_gain_f32``)."""
+        _require_cuda(wav, "audio")
+        dev = wav.device
+        if offsets is not None:
+            flat = wav.reshape(-1).float().contiguous()
+            off = offsets.to(device=dev, dtype=torch.int64).contiguous()
+            rows, b, n, stride = flat, int(n_rows), int(max_samples), int(max_samples)
+        else:
+            rows = as_rows(wav)
+            b, n = rows.shape
+            stride, off = (rows.stride(0) if b > 1 else n), None
+        gain = torch.empty((b,), dtype=torch.float32, device=dev)
+        len_ptr, _keep = self._lengths_ptr(lengths, b, dev)
+        with torch.cuda.device(dev):
+            _native.check(_native.load().dmel_row_peak_gain_f32(
+                rows.data_ptr(), b, n, stride, off.data_ptr() if off is not None else None, len_ptr, float(target),
+                gain.data_ptr(), _stream_ptr(dev)))
+        return gain
+
     # -- helpers --------------------------------------------------------------
     def _frames_or_raise(self, n_samples: int) -> int:
         pad = (self.n_fft - self.hop_length) // 2

@@ -57,12 +57,14 @@ class DMelQuantizer(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() move the buffers
         self._invalidate()
+        lo32, hi32 = self.lo, self.hi
         out = super()._apply(fn, *args, **kwargs)
         # .half() / .bfloat16() / .double() on a parent module would cast the statistics too; the kernels read them
-        # as float32 and the bin edges are defined in float32, so only the device follows such a call
+        # as float32 and the bin edges are defined in float32, so only the DEVICE follows such a call: the float32
+        # values are carried over unrounded
         if self.lo.dtype != torch.float32:
-            self.lo = self.lo.to(torch.float32)
-            self.hi = self.hi.to(torch.float32)
+            self.lo = lo32.to(self.lo.device)
+            self.hi = hi32.to(self.hi.device)
         return out
 
     def _load_from_state_dict(self, *args, **kwargs):
@@ -230,6 +232,54 @@ class DMelTokenizer(nn.Module):
         if return_mel:
             return out[0], code_lengths, out[1]
         return out, code_lengths
+
+    @torch.no_grad()
+    def encode_utterances(self, audios, audio_lengths: Optional[Tensor] = None, *, peak_normalize: Optional[float] = None,
+                          return_mel: bool = False):
+        """Encode every utterance as if the reference ran on it ALONE, without the host-side steps of the reference's
+        data module (dataset/lhotse_tts_dataset.py:29-33 peak normalisation, :46-65 right-pad collate):
+
+        * ``audios`` is a list of 1-D waveforms of different lengths (a ragged batch: they are packed back to back,
+          no padding is stored or transformed), or a padded (B, L) / (B, 1, L) tensor with ``audio_lengths``;
+        * the reflect padding happens at each utterance's own end and it has ``length // hop`` frames;
+        * ``peak_normalize=0.95`` applies ``x / max|x| * 0.95`` per utterance on the GPU (one extra pass over the
+          waveform, the normalised audio never exists in HBM).
+
+        -> (codes (B, n_mels, T_max) uint8 zero past each utterance, code_lengths (B,)[, log-mel])."""
+        q = self.quantizer
+        q._check_ready()
+        dev = q.lo.device
+        plan = self._plan(dev)
+        if isinstance(audios, (list, tuple)):
+            lens = [int(a.numel()) for a in audios]
+            # 16-byte aligned starts keep the bulk-copy path: round every utterance up to 4 samples inside the buffer
+            starts, total = [], 0
+            for n in lens:
+                starts.append(total)
+                total += (n + 3) // 4 * 4
+            flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            for a, s0, n in zip(audios, starts, lens):
+                flat[s0:s0 + n] = a.reshape(-1).to(device=dev, dtype=torch.float32)
+            # row b = the first lengths[b] samples at offsets[b]; the slack up to offsets[b + 1] is never read
+            offsets = torch.tensor(starts + [total], dtype=torch.int64, device=dev)
+            lengths = torch.tensor(lens, dtype=torch.int32, device=dev)
+            kw = dict(offsets=offsets, n_rows=len(lens), max_samples=max(lens), min_samples=min(lens), lengths=lengths)
+            wav = flat
+        else:
+            if audio_lengths is None:
+                raise ValueError("a padded batch needs audio_lengths to be treated utterance by utterance")
+            lengths = self._flat_lengths(audio_lengths).to(dev)
+            lens = lengths.tolist()
+            kw = dict(lengths=lengths, own_length=True, min_samples=min(lens))
+            wav = audios
+        gain = None
+        if peak_normalize is not None:
+            gain = plan.peak_gain(wav, lengths=kw["lengths"], offsets=kw.get("offsets"), n_rows=kw.get("n_rows"),
+                                  max_samples=kw.get("max_samples"), target=float(peak_normalize))
+        out = plan.run(wav, row_gain=gain, lo=q.lo, scale=q.scale(), n_bins=q.n_bins, want_codes=True,
+                       want_logmel=return_mel, mask_invalid=True, **kw)
+        code_lengths = torch.div(kw["lengths"], self.hop_length, rounding_mode="floor")
+        return (out["codes"], code_lengths, out["logmel"]) if return_mel else (out["codes"], code_lengths)
 
     @torch.no_grad()
     def encode_decode(self, audios: Tensor, audio_lengths: Optional[Tensor] = None) -> DMelResult:

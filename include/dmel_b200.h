@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DMEL_ABI_VERSION 7
+#define DMEL_ABI_VERSION 8
 
 #define DMEL_OK 0
 #define DMEL_ERR_INVALID (-1)     /* bad argument (shape, null pointer, L <= reflect pad ...) */
@@ -187,6 +187,64 @@ int dmel_encode_host_pcm16_u8(dmel_plan* plan, const int16_t* wav_host, long lon
                               long long row_stride, const int32_t* lengths_host,
                               const float* lo_host, const float* scale_host, int n_bins,
                               uint8_t* codes_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * The general entry point: every input layout and every output of the fused kernel in one call.
+ * The functions above are this call with a few fields filled in.
+ *
+ * Input layouts
+ *   padded   wav_dev is (n_rows, row_stride >= n_samples): what the reference's collate yields
+ *            (reference dataset/lhotse_tts_dataset.py:46-65, right zero-padded rows).
+ *   ragged   offsets_dev != NULL: row b is wav_dev[offsets[b] .. offsets[b+1]) (n_rows + 1 int64 entries,
+ *            device memory), n_samples = the longest row; no padding is stored or read.  Offsets that are
+ *            multiples of 4 samples (8 for int16) keep the bulk-copy fast path; to align them, leave slack
+ *            between rows and pass lengths_dev as well: row b is then the first lengths[b] samples at offsets[b].
+ *   own_length = 1 (implied by ragged): each row is an utterance of its own length (lengths_dev[b], or the
+ *            offsets' difference) and is transformed as if the reference ran on it ALONE: the reflect padding
+ *            happens at the utterance's own end, it has lengths[b] / hop frames, everything past them is written
+ *            as 0.  With own_length = 0 and lengths_dev the reference's behaviour on the padded batch is kept
+ *            (reflection at the end of the padded row, utils/spectrogram.py:58-62 sees the collated tensor).
+ *            min_row_samples: the caller's lower bound on the row lengths; must exceed the reflect pad
+ *            (the reference's F.pad raises otherwise) - the library cannot read device-side lengths.
+ *   row_gain_dev  per-row gain applied to the samples (float32 input only): per-utterance peak normalisation,
+ *            reference dataset/lhotse_tts_dataset.py:29-33; fill it with dmel_row_peak_gain_f32.
+ * Outputs: any subset of codes (+ bin centres), log-mel (float32 / bfloat16, optionally masked), running
+ * min / max; all (n_rows, n_mels, T) with T = dmel_plan_num_frames(plan, n_samples).  Statistics and codes
+ * cannot be asked for in one call (calibration precedes quantisation). */
+typedef struct dmel_io {
+  size_t struct_size;            /* sizeof(dmel_io): lets the library reject a caller built against another layout */
+  const void* wav_dev;           /* float32, or int16 PCM with wav_is_pcm16 = 1 */
+  int wav_is_pcm16;
+  long long n_rows, n_samples, row_stride;
+  const long long* offsets_dev;  /* ragged layout, or NULL */
+  const int32_t* lengths_dev;    /* valid samples per row, or NULL */
+  int own_length;
+  long long min_row_samples;     /* only read with own_length / ragged */
+  const float* row_gain_dev;     /* or NULL */
+  /* quantiser (needed for codes_dev) */
+  const float* lo_dev;
+  const float* scale_dev;
+  const float* step_dev;         /* needed for mel_hat_dev */
+  int n_bins;
+  /* outputs, NULL to skip */
+  uint8_t* codes_dev;
+  float* mel_hat_dev;            /* bin centre of every code (needs codes_dev) */
+  void* logmel_dev;              /* float32, or bfloat16 with logmel_is_bf16 = 1 */
+  int logmel_is_bf16;
+  int mask_invalid;              /* log-mel of frames at or past lengths[b] / hop written as 0 */
+  float* min_dev;                /* running per-channel min / max, updated in place */
+  float* max_dev;
+} dmel_io;
+
+int dmel_run(dmel_plan* plan, const dmel_io* io, void* stream);
+
+/* gain_dev[b] = target_peak / max|x| over the valid samples of row b (a peak below FLT_MIN counts as 1):
+ * the gain of `librosa.util.normalize(audio) * 0.95` (reference dataset/lhotse_tts_dataset.py:32) with
+ * target_peak = 0.95.  One HBM-bound pass over the waveform (4 bytes per sample) and a tiny second launch;
+ * padded (offsets_dev NULL) or ragged layout as in dmel_io; lengths_dev may be NULL. */
+int dmel_row_peak_gain_f32(const float* wav_dev, long long n_rows, long long n_samples, long long row_stride,
+                           const long long* offsets_dev, const int32_t* lengths_dev, float target_peak,
+                           float* gain_dev, void* stream);
 
 /* Stand-alone quantiser stages on an existing (B, n_mels, T) log-mel tensor. */
 int dmel_quantize_u8(const float* logmel_dev, long long n_rows, int n_mels, long long n_frames,

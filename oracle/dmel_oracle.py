@@ -221,3 +221,29 @@ def dmel_tokenize(wav: torch.Tensor, cfg: MelConfig, lo: torch.Tensor, hi: torch
                   bank: Optional[torch.Tensor] = None) -> torch.Tensor:
     """waveform -> uint8 codes, the whole path on the CPU."""
     return dmel_encode(log_mel(wav, cfg, bank), lo, hi, n_bins)
+
+
+# --------------------------------------------------------------------------- #
+# input side of the path, as the reference's data module does it on the host
+# --------------------------------------------------------------------------- #
+def peak_normalize(audio: torch.Tensor, target: float = 0.95) -> torch.Tensor:
+    """``librosa.util.normalize(audio) * 0.95`` (reference dataset/lhotse_tts_dataset.py:32) for one 1-D utterance:
+    x / max|x| in float32, then * 0.95; librosa treats a peak below the smallest normal float as 1."""
+    x = audio.to(torch.float32)
+    peak = x.abs().max()
+    if peak.item() < torch.finfo(torch.float32).tiny:
+        peak = torch.ones_like(peak)
+    return (x / peak) * torch.tensor(target, dtype=torch.float32)
+
+
+def log_mel_each(utterances, cfg: MelConfig, bank: Optional[torch.Tensor] = None, peak: Optional[float] = None):
+    """The reference transform run on every utterance ALONE (what a batch size of 1 gives: reflect padding at
+    the utterance's own ends, ``len // hop`` frames); optionally after the data module's peak normalisation.
+    -> list of (n_mels, T_u) tensors."""
+    out = []
+    for u in utterances:
+        x = u.reshape(-1).to(torch.float32)
+        if peak is not None:
+            x = peak_normalize(x, peak)
+        out.append(log_mel(x[None, None, :], cfg, bank)[0])
+    return out

@@ -4,7 +4,9 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_GEOMETRY, oracle_config
+import os
+
+from conftest import GOLDEN_GEOMETRY, ROOT, oracle_config
 from dmel_codec_b200 import filters, synth
 from oracle import dmel_oracle as O
 
@@ -126,3 +128,39 @@ def test_synth_is_seeded_and_bounded():
     assert torch.equal(a, b) and a.abs().max() <= 0.95 + 1e-6
     assert not torch.equal(a, synth.utterance(6, 4000, 16000))
     assert (a == 0).sum() >= 4000 // 20  # the silent span
+
+
+# ---------------------------------------------------------------------------
+# the quantiser spec is frozen: tests/golden/quantizer_golden.npz (plain numpy, make_quantizer_golden.py)
+# ---------------------------------------------------------------------------
+QUANT_CASES = ["cfg1_16k_80", "cfg2_24k_128", "cfg5_44k_160", "yaml_24k_100", "short_window"]
+
+
+@pytest.fixture(scope="module")
+def quant_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "quantizer_golden.npz"))
+
+
+@pytest.mark.parametrize("name", QUANT_CASES)
+def test_oracle_quantiser_reproduces_the_frozen_spec(golden, quant_golden, name):
+    mel = torch.from_numpy(golden[name + "/logmel"])
+    k = int(quant_golden[name + "/n_bins"])
+    lo, hi = O.calibrate_minmax(mel)
+    assert torch.equal(lo, torch.from_numpy(quant_golden[name + "/lo"])) and torch.equal(hi, torch.from_numpy(quant_golden[name + "/hi"]))
+    assert torch.equal(O.bin_scale(lo, hi, k), torch.from_numpy(quant_golden[name + "/scale"]))
+    codes = O.dmel_encode(mel, lo, hi, k)
+    assert torch.equal(codes, torch.from_numpy(quant_golden[name + "/codes"]))
+    assert torch.equal(O.dmel_decode_table(lo, hi, k), torch.from_numpy(quant_golden[name + "/table"]))
+    assert torch.equal(O.dmel_decode(codes, lo, hi, k), torch.from_numpy(quant_golden[name + "/decoded"]))
+
+
+def test_oracle_quantiser_edge_cases_match_the_frozen_spec(quant_golden):
+    """degenerate channel, value == hi / lo, values on and one ulp around every interior edge, out-of-range values"""
+    mel = torch.from_numpy(quant_golden["edges/mel"])
+    lo, hi = torch.from_numpy(quant_golden["edges/lo"]), torch.from_numpy(quant_golden["edges/hi"])
+    codes = O.dmel_encode(mel, lo, hi, 16)
+    assert torch.equal(codes, torch.from_numpy(quant_golden["edges/codes"]))
+    assert torch.equal(O.dmel_decode(codes, lo, hi, 16), torch.from_numpy(quant_golden["edges/decoded"]))
+    assert torch.all(codes[0, 0] == 0)                 # degenerate channel: scale 0, every code 0
+    assert torch.all(codes[0, 1:, 1] == 15)            # x == hi lands in the last bin
+    assert torch.all(codes[0, 1:, 0] == 0) and torch.all(codes[0, 1:, 2] == 0) and torch.all(codes[0, 1:, 3] == 15)
