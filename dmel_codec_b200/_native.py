@@ -63,6 +63,9 @@ SIGNATURES = {
                                  c_longlong, POINTER(c_longlong), c_void_p]),
     "dmel_stream_flush": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_longlong, POINTER(c_longlong),
                                   c_void_p]),
+    "dmel_stream_bind": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "dmel_stream_input": (c_int, [c_void_p, c_longlong, POINTER(c_void_p), POINTER(c_longlong)]),
+    "dmel_stream_commit": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, POINTER(c_longlong)]),
     "dmel_encode_host_u8": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_void_p,
                                     c_void_p, c_void_p, c_int, c_void_p]),
     "dmel_encode_host_pcm16_u8": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_void_p,

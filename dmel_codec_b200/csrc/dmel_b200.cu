@@ -728,6 +728,11 @@ struct dmel_stream {
   long long base = 0;      // virtual sample index of buf[:, 0]
   long long seen = 0;      // samples received per stream
   long long t_next = 0;    // next frame to emit
+  // quantiser and CUDA stream bound once (dmel_stream_bind) so that the per-chunk call carries four arguments
+  const float* lo_dev = nullptr;
+  const float* scale_dev = nullptr;
+  int n_bins = 0;
+  void* cuda_stream = nullptr;
 };
 
 namespace {
@@ -800,6 +805,28 @@ long long dmel_stream_pending(const dmel_stream* s, long long n_incoming, int at
   return std::max<long long>(t_end - s->t_next, 0);
 }
 
+// make room for n more samples per stream (drops what no future frame needs) and say where they go
+static int stream_reserve(dmel_stream* s, long long n, cudaStream_t st) {
+  if (s->seen - s->base + n <= s->capacity) return DMEL_OK;
+  long long keep_from = std::max<long long>(0, s->t_next * s->plan->hop - s->plan->pad_inner) / 4 * 4;
+  keep_from = std::max(keep_from, s->base);
+  const long long live = s->seen - keep_from, shift = keep_from - s->base;
+  if (live + n > s->capacity)
+    return fail(DMEL_ERR_INVALID, "chunk of %lld samples does not fit a stream buffer of %lld (%lld live)", n, s->capacity, live);
+  if (shift > 0 && live > 0) {
+    const size_t pitch = (size_t)s->capacity * sizeof(float), width = (size_t)live * sizeof(float);
+    if (live <= shift) {
+      DMEL_CUDA(cudaMemcpy2DAsync(s->buf, pitch, s->buf + shift, pitch, width, s->n_streams, cudaMemcpyDeviceToDevice, st));
+    } else {  // source and destination overlap: go through the scratch copy
+      if (!s->scratch) DMEL_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->scratch), (size_t)s->n_streams * pitch));
+      DMEL_CUDA(cudaMemcpy2DAsync(s->scratch, pitch, s->buf + shift, pitch, width, s->n_streams, cudaMemcpyDeviceToDevice, st));
+      DMEL_CUDA(cudaMemcpy2DAsync(s->buf, pitch, s->scratch, pitch, width, s->n_streams, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  s->base = keep_from;
+  return DMEL_OK;
+}
+
 int dmel_stream_push(dmel_stream* s, const float* chunk, long long n, long long chunk_stride,
                      const float* lo_dev, const float* scale_dev, int n_bins, uint8_t* codes_dev,
                      long long codes_frames, long long* n_frames_out, void* stream) {
@@ -809,25 +836,9 @@ int dmel_stream_push(dmel_stream* s, const float* chunk, long long n, long long 
     return fail(DMEL_ERR_INVALID, "bad chunk: n=%lld stride=%lld", n, chunk_stride);
   cudaStream_t st = (cudaStream_t)stream;
   DeviceGuard guard(s->plan->device);
-  if (s->seen - s->base + n > s->capacity) {
-    // drop the samples no future frame needs; the new base stays 16-byte aligned
-    long long keep_from = std::max<long long>(0, s->t_next * s->plan->hop - s->plan->pad_inner) / 4 * 4;
-    keep_from = std::max(keep_from, s->base);
-    const long long live = s->seen - keep_from, shift = keep_from - s->base;
-    if (live + n > s->capacity)
-      return fail(DMEL_ERR_INVALID, "chunk of %lld samples does not fit a stream buffer of %lld (%lld live)", n,
-                  s->capacity, live);
-    if (shift > 0 && live > 0) {
-      const size_t pitch = (size_t)s->capacity * sizeof(float), width = (size_t)live * sizeof(float);
-      if (live <= shift) {
-        DMEL_CUDA(cudaMemcpy2DAsync(s->buf, pitch, s->buf + shift, pitch, width, s->n_streams, cudaMemcpyDeviceToDevice, st));
-      } else {  // source and destination overlap: go through the scratch copy
-        if (!s->scratch) DMEL_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->scratch), (size_t)s->n_streams * pitch));
-        DMEL_CUDA(cudaMemcpy2DAsync(s->scratch, pitch, s->buf + shift, pitch, width, s->n_streams, cudaMemcpyDeviceToDevice, st));
-        DMEL_CUDA(cudaMemcpy2DAsync(s->buf, pitch, s->scratch, pitch, width, s->n_streams, cudaMemcpyDeviceToDevice, st));
-      }
-    }
-    s->base = keep_from;
+  {
+    int rc_reserve = stream_reserve(s, n, st);  // drops the samples no future frame needs; the new base stays 16-byte aligned
+    if (rc_reserve != DMEL_OK) return rc_reserve;
   }
   if (n > 0) {
     float* dst = s->buf + (s->seen - s->base);
@@ -841,6 +852,39 @@ int dmel_stream_push(dmel_stream* s, const float* chunk, long long n, long long 
   }
   return stream_emit(s, stream_frames_ready(s, s->seen), lo_dev, scale_dev, n_bins, codes_dev, codes_frames, n_frames_out,
                      stream);
+}
+
+int dmel_stream_bind(dmel_stream* s, const float* lo_dev, const float* scale_dev, int n_bins, void* stream) {
+  if (!s) return fail(DMEL_ERR_INVALID, "stream is null");
+  if (!lo_dev || !scale_dev) return fail(DMEL_ERR_INVALID, "lo_dev / scale_dev is null");
+  int rc = check_bins(n_bins);
+  if (rc != DMEL_OK) return rc;
+  s->lo_dev = lo_dev;
+  s->scale_dev = scale_dev;
+  s->n_bins = n_bins;
+  s->cuda_stream = stream;
+  return DMEL_OK;
+}
+
+int dmel_stream_input(dmel_stream* s, long long n, float** where_dev, long long* row_stride) {
+  if (!s || !where_dev) return fail(DMEL_ERR_INVALID, "stream / where_dev is null");
+  if (n <= 0) return fail(DMEL_ERR_INVALID, "bad chunk length %lld", n);
+  DeviceGuard guard(s->plan->device);
+  int rc = stream_reserve(s, n, (cudaStream_t)s->cuda_stream);
+  if (rc != DMEL_OK) return rc;
+  *where_dev = s->buf + (s->seen - s->base);
+  if (row_stride) *row_stride = s->capacity;
+  return DMEL_OK;
+}
+
+int dmel_stream_commit(dmel_stream* s, long long n, uint8_t* codes_dev, long long codes_frames, long long* n_frames_out) {
+  if (!s) return fail(DMEL_ERR_INVALID, "stream is null");
+  if (n_frames_out) *n_frames_out = 0;
+  if (!s->lo_dev) return fail(DMEL_ERR_INVALID, "call dmel_stream_bind first");
+  if (n < 0 || s->seen - s->base + n > s->capacity) return fail(DMEL_ERR_INVALID, "commit of %lld samples without a matching dmel_stream_input", n);
+  s->seen += n;
+  return stream_emit(s, stream_frames_ready(s, s->seen), s->lo_dev, s->scale_dev, s->n_bins, codes_dev, codes_frames, n_frames_out,
+                     s->cuda_stream);
 }
 
 int dmel_stream_flush(dmel_stream* s, const float* lo_dev, const float* scale_dev, int n_bins, uint8_t* codes_dev,

@@ -103,6 +103,40 @@ class DMelStreamEncoder:
         self._t_next += count
         return out
 
+    # -- zero-copy chunks: the producer writes straight into the history buffer -----------------------------
+    def input_view(self, n: int) -> torch.Tensor:
+        """(n_streams, n) float32 CUDA view of where the next ``n`` samples of every stream belong (a window of the
+        library's history buffer).  Fill it (a kernel of the producer, or a host-to-device copy straight into it),
+        then ``commit(n)``: one kernel launch per chunk, no copy of the chunk."""
+        if not getattr(self, "_bound", False):
+            q = self.tok.quantizer
+            self._lo, self._scale = q.lo, q.scale()  # kept alive: the library holds their addresses
+            _native.check(self._lib.dmel_stream_bind(self._handle, self._lo.data_ptr(), self._scale.data_ptr(), q.n_bins,
+                                                     torch.cuda.current_stream(self.device).cuda_stream))
+            self._where, self._stride = ctypes.c_void_p(), ctypes.c_longlong()
+            self._bound, self._views = True, {}
+        _native.check(self._lib.dmel_stream_input(self._handle, n, ctypes.byref(self._where), ctypes.byref(self._stride)))
+        key = (self._where.value, n)
+        view = self._views.get(key)
+        if view is None:  # wrap the device window as a tensor once per distinct (address, length)
+            if len(self._views) > 4096:
+                self._views.clear()
+            view = _device_view(self._where.value, self.n_streams, n, self._stride.value, self.device)
+            self._views[key] = view
+        return view
+
+    def commit(self, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Encode every frame completed by the ``n`` samples written into ``input_view(n)``."""
+        count = self.frames_after(n)
+        if out is None:
+            out = torch.empty((self.n_streams, self.tok.quantizer.n_mels, count), dtype=torch.uint8, device=self.device)
+        elif out.shape[2] != count or out.dtype != torch.uint8 or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous uint8 tensor with {count} frames")
+        _native.check(self._lib.dmel_stream_commit(self._handle, n, out.data_ptr(), count, self._count_ref))
+        self._seen += n
+        self._t_next += count
+        return out
+
     def flush(self) -> torch.Tensor:
         """End of stream: emit the remaining frames (they use the reference's right-edge
         reflection) and reset.  Total frames over the stream's life = n_samples // hop."""
@@ -114,3 +148,16 @@ class DMelStreamEncoder:
             self._count_ref, torch.cuda.current_stream(self.device).cuda_stream))
         self._seen = self._t_next = 0  # the library resets the stream after a flush
         return codes
+
+
+class _DevicePtr:
+    """Minimal ``__cuda_array_interface__`` carrier: lets torch wrap a window of library-owned device memory."""
+
+    def __init__(self, ptr: int, shape, strides_bytes):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 3,
+                                         "strides": tuple(strides_bytes)}
+
+
+def _device_view(ptr: int, rows: int, n: int, row_stride: int, device: torch.device) -> torch.Tensor:
+    with torch.cuda.device(device):
+        return torch.as_tensor(_DevicePtr(ptr, (rows, n), (row_stride * 4, 4)), device=device)

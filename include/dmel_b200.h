@@ -174,6 +174,14 @@ int dmel_stream_push(dmel_stream* s, const float* chunk, long long n, long long 
 int dmel_stream_flush(dmel_stream* s, const float* lo_dev, const float* scale_dev, int n_bins,
                       uint8_t* codes_dev, long long codes_frames, long long* n_frames_out, void* stream);
 
+/* Zero-copy form of a push for latency-bound callers (80 ms chunks): bind the quantiser and the CUDA stream once,
+ * then per chunk ask where the next n samples of every stream go (a window of the library's history buffer:
+ * where_dev[stream * row_stride + i]), have the producer write them there, and commit - ONE kernel launch, no
+ * chunk copy, four arguments.  Same codes as dmel_stream_push. */
+int dmel_stream_bind(dmel_stream* s, const float* lo_dev, const float* scale_dev, int n_bins, void* stream);
+int dmel_stream_input(dmel_stream* s, long long n, float** where_dev, long long* row_stride);
+int dmel_stream_commit(dmel_stream* s, long long n, uint8_t* codes_dev, long long codes_frames, long long* n_frames_out);
+
 /* Same as dmel_encode_u8 with HOST buffers: chunks rows through pinned staging,
  * overlapping H2D, kernel and D2H on internal streams; returns when codes_host
  * is complete.  lengths_host may be NULL; lo/scale are host arrays too. */

@@ -364,3 +364,32 @@ def test_ragged_batch_rejects_an_utterance_shorter_than_the_reflect_pad(d):
     tok.quantizer.set_stats(torch.full((80,), -11.0), torch.full((80,), 2.0))
     with pytest.raises(ValueError, match="reflect"):
         tok.encode_utterances([torch.zeros(4000).cuda(), torch.zeros(384).cuda()])
+
+
+def test_zero_copy_streaming_equals_offline(d):
+    """input_view / commit (the producer writes straight into the history buffer, one launch per chunk) emits the
+    same codes as the offline encode of the whole waveform, across buffer compactions."""
+    from dmel_codec_b200 import synth
+    kw = GOLDEN_GEOMETRY["cfg1_16k_80"]
+    n = 16000 * 6 + 77
+    wav = synth.batch([31, 32], n, 16000, "speech").cuda()
+    tok = _tokenizer(d, kw, 16)
+    tok.calibrate([wav])
+    want, _ = tok.encode(wav)
+    enc = d.DMelStreamEncoder(tok, n_streams=2, capacity_samples=8192)  # small: forces compaction every few chunks
+    got, pos = [], 0
+    for size in [1280] * 40 + [700, 3000, 333]:
+        size = min(size, n - pos)
+        if size <= 0:
+            break
+        view = enc.input_view(size)
+        assert view.shape == (2, size) and view.is_cuda
+        view.copy_(wav[:, 0, pos:pos + size])
+        got.append(enc.commit(size))
+        pos += size
+    while pos < n:  # the rest through the copying push: both forms share the state
+        size = min(1280, n - pos)
+        got.append(enc.push(wav[:, 0, pos:pos + size]))
+        pos += size
+    got.append(enc.flush())
+    assert torch.equal(torch.cat(got, dim=2), want)
