@@ -506,7 +506,8 @@ def stream_workload(dev):
     geom = dict(sample_rate=16000, n_fft=1024, win_length=1024, hop_length=256, n_mels=80)
     tok = d.DMelTokenizer(n_bins=16, **geom).to(dev)
     wav = synth.batch([0], 16000 * 30, 16000, "speech").to(dev)
-    tok.calibrate([wav])
+    tok.quantizer.reset_stats()
+    tok.update_stats(wav)  # local statistics only: this workload runs on rank 0 alone, so NO collective may be called here
     enc = d.DMelStreamEncoder(tok, n_streams=1, capacity_samples=1 << 16)
     chunk, lat = 1280, []
     n_chunks = wav.shape[2] // chunk
@@ -674,7 +675,8 @@ def run_pool_workload(args, name):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=240))
     out = pool_workload(name, rank, world, dev)
     if rank == 0:
         print(json.dumps(out))
@@ -714,7 +716,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=240))  # a mismatched collective fails in minutes, not in ten
     try:
         run_ours(args, rank, world, local_rank)
     finally:
