@@ -263,20 +263,17 @@ def median_window_ms(run_window, reps: int, stream) -> list:
     return [marks[r].elapsed_time(marks[r + 1]) for r in range(reps)]
 
 
-def time_kernel_ms(fn, reps: int, stream, flush=None) -> float:
-    """Median device time of one call of fn(i), each call between two events; `flush` (if given) runs before every
-    call outside the timed pair to evict the previous call's data from L2."""
-    ms = []
-    for i in range(reps):
-        if flush is not None:
-            flush()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+def time_kernel_ms(fn, reps: int, stream) -> float:
+    """Median device time of one call of fn(i): every call sits between its own pair of events, the calls are queued
+    back to back and the host synchronises once at the end, so the GPU never idles between them (a launch timed from
+    an idle GPU carries ~15 us of ramp that no pipeline ever sees)."""
+    marks = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for i, (e0, e1) in enumerate(marks):
         e0.record(stream)
         fn(i)
         e1.record(stream)
-        e1.synchronize()
-        ms.append(e0.elapsed_time(e1))
-    return statistics.median(ms)
+    torch.cuda.synchronize()
+    return statistics.median(e0.elapsed_time(e1) for e0, e1 in marks)
 
 
 def run_ours(args, rank: int, world: int, local_rank: int):

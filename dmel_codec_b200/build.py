@@ -24,7 +24,7 @@ OBJ_DIR = os.path.join(HERE, "_obj", os.path.splitext(os.path.basename(OUT))[0])
 # (n_fft, frames per tile, CTAs per SM): must match kVariants in csrc/dmel_b200.cu
 VARIANTS = [(1024, 8, 3), (1024, 16, 2), (1024, 8, 2), (1024, 16, 1), (1024, 8, 1),
             (2048, 8, 2), (2048, 16, 1), (2048, 8, 1)]
-DEPS = ["dmel_b200.cu", "fused_variant.cu", "fused_variants.h", "launch_util.cuh", "logmel_kernel.cuh",
+DEPS = ["dmel_b200.cu", "fused_variant.cu", "fused_ws_variant.cu", "ws_kernel.cuh", "fused_variants.h", "launch_util.cuh", "logmel_kernel.cuh",
         "fft_core.cuh", "fastdiv.cuh", "codec_kernels.cuh", "extras_kernels.cuh",
         os.path.join("..", "..", "include", "dmel_b200.h")]
 NVCC_FLAGS = ["-std=c++20", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -50,6 +50,7 @@ def _file_hash(paths) -> str:
                 h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     h.update(os.environ.get("DMEL_NVCC_EXTRA", "").encode())
+    h.update(os.environ.get("DMEL_BUILD_WS", "").encode())
     return h.hexdigest()
 
 
@@ -94,6 +95,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for n_fft, tf, occ in VARIANTS:
         jobs.append(("fused_variant.cu", os.path.join(OBJ_DIR, f"fused_{n_fft}_{tf}_{occ}.o"),
                      [f"-DDMEL_V_NFFT={n_fft}", f"-DDMEL_V_TF={tf}", f"-DDMEL_V_OCC={occ}"]))
+    if os.environ.get("DMEL_BUILD_WS"):  # the warp-specialised experiment (ws_kernel.cuh): measured slower, not built by default
+        jobs.append(("fused_ws_variant.cu", os.path.join(OBJ_DIR, "fused_ws_1024.o"), []))
+        jobs[0] = (jobs[0][0], jobs[0][1], ["-DDMEL_WITH_WS"])
     workers = int(os.environ.get("DMEL_BUILD_JOBS", "0")) or min(len(jobs), os.cpu_count() or 4)
     with ThreadPoolExecutor(max_workers=workers) as pool:
         logs = list(pool.map(lambda j: _compile(nvcc, j[0], j[1], j[2], verbose), jobs))

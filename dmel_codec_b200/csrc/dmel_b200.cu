@@ -98,6 +98,9 @@ using dmel::FusedParams;
 
 // The kernel variants this build carries, most CTAs per SM first (one translation unit each: fused_variant.cu).
 const dmel::VariantOps* const kVariants[] = {
+#ifdef DMEL_WITH_WS
+    &dmel::kVariant_ws_1024,  // warp-specialised experiment (ws_kernel.cuh; build with DMEL_BUILD_WS=1, select with DMEL_WS=1)
+#endif
     &dmel::kVariant_1024_8_3, &dmel::kVariant_1024_16_2, &dmel::kVariant_1024_8_2, &dmel::kVariant_1024_16_1,
     &dmel::kVariant_1024_8_1, &dmel::kVariant_2048_8_2,  &dmel::kVariant_2048_16_1, &dmel::kVariant_2048_8_1};
 
@@ -167,12 +170,11 @@ void band_filterbank(const float* basis, int n_mels, int n_freq, int lanes, std:
   }
 }
 
-// Deals the channel groups to the 8 warps of a CTA so that every warp runs about the same number of bin-loop
-// steps in the mel phase (longest group first, always to the least loaded warp).  Warp 0 starts with a handicap:
-// one of its threads describes the next tile and starts its copy while the others are already in the mel phase.
-// order[r * 8 + w] = group of warp w in its r-th trip, -1 = none.
-std::vector<int> deal_groups(const std::vector<int>& group_steps) {
-  constexpr int kW = dmel::kWarps;
+// Deals the channel groups to the kW warps that run the mel phase so that every one of them runs about the same
+// number of bin-loop steps (longest group first, always to the least loaded warp).  With `handicap`, warp 0 starts
+// with a load: one of its threads describes the next tile and starts its copy while the others are already in the
+// mel phase.  order[r * kW + w] = group of warp w in its r-th trip, -1 = none.
+std::vector<int> deal_groups(const std::vector<int>& group_steps, int kW, bool handicap) {
   const int kEpilogue = 3, kHandicap = 5;  // in steps: fixed cost per group (records, log, quantise, stores); warp 0's extra work
   std::vector<int> idx(group_steps.size());
   for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
@@ -184,10 +186,8 @@ std::vector<int> deal_groups(const std::vector<int>& group_steps) {
   }
   std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return group_steps[a] > group_steps[b]; });
   std::vector<std::vector<int>> mine(kW);
-  int load[kW] = {};
-  int book = 0;
-  if (const char* env = std::getenv("DMEL_BOOK_WARP")) book = std::atoi(env) & (kW - 1);  // measurements: which warp carries the bookkeeping thread
-  load[book] = kHandicap;
+  std::vector<int> load(kW, 0);
+  if (handicap) load[0] = kHandicap;
   for (int g : idx) {
     int w = 0;
     for (int k = 1; k < kW; ++k)
@@ -369,13 +369,19 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
   // pins the CTAs-per-SM choice (experiments)
   const char* occ_env = std::getenv("DMEL_OCC");
   const int occ_pin = occ_env ? std::atoi(occ_env) : 0;
+  const char* ws_env = std::getenv("DMEL_WS");
+  const bool ws_on = ws_env ? std::atoi(ws_env) != 0 : false;  // off: it measured 115 us per step against 92.6 (profiles/history.md)
+  (void)ws_on;
   std::vector<int4> chan;
   std::vector<float> weights;
   std::vector<int> group_steps, order;
   for (const dmel::VariantOps* v : kVariants) {
     if (v->n_fft != n_fft || (occ_pin && v->occ != occ_pin)) continue;
+#ifdef DMEL_WITH_WS
+    if (v == &dmel::kVariant_ws_1024 && (occ_pin || !ws_on || center)) continue;
+#endif
     band_filterbank(mel_basis_host, n_mels, n_fft / 2 + 1, 32 / v->tf, &chan, &weights, &group_steps);
-    order = deal_groups(group_steps);
+    order = deal_groups(group_steps, v->mel_warps, v->mel_warps == dmel::kWarps);
     const int wave_len = ((v->tf - 1) * hop_length + n_fft + 7) / 8 * 8;  // whole 16-byte units of float and of int16
     const size_t need = v->smem_need(wave_len, (int)chan.size(), (int)weights.size(), (int)order.size());
     const size_t limit = std::min<size_t>((size_t)max_sm_smem / v->occ - 1024, (size_t)plan->max_smem);  // 1 KB/CTA reserved

@@ -77,7 +77,7 @@ cudaError_t launch(int mode, const FusedParams& p, int grid, size_t smem_bytes, 
 
 #define DMEL_CAT_(a, b, c, d) a##b##_##c##_##d
 #define DMEL_CAT(a, b, c, d) DMEL_CAT_(a, b, c, d)
-extern const VariantOps DMEL_CAT(kVariant_, DMEL_V_NFFT, DMEL_V_TF, DMEL_V_OCC) = {NFFT, TF, OCC, kLeanVariant, smem_need,
+extern const VariantOps DMEL_CAT(kVariant_, DMEL_V_NFFT, DMEL_V_TF, DMEL_V_OCC) = {NFFT, TF, OCC, kLeanVariant, kWarps, smem_need,
                                                                                   fill_offsets, launch};
 
 }  // namespace dmel

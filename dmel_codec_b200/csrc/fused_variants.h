@@ -12,6 +12,7 @@ struct FusedParams;
 struct VariantOps {
   int n_fft, tf, occ;  // transform size, frames per tile, CTAs per SM the variant is built for
   bool lean;           // register-lean variant (the only ones with int16 PCM input)
+  int mel_warps;       // warps that run the mel phase (the channel groups are dealt to this many)
   size_t (*smem_need)(int wave_len, int n_chan, int nnz, int n_order);
   void (*fill_offsets)(FusedParams* p);
   // mode = OR of the kOut* / kIn* bits of logmel_kernel.cuh; cudaErrorInvalidValue for a combination that is not built
@@ -21,5 +22,6 @@ struct VariantOps {
 // most CTAs per SM first: dmel_plan_create takes the first whose shared memory fits
 extern const VariantOps kVariant_1024_8_3, kVariant_1024_16_2, kVariant_1024_8_2, kVariant_1024_16_1, kVariant_1024_8_1;
 extern const VariantOps kVariant_2048_8_2, kVariant_2048_16_1, kVariant_2048_8_1;
+extern const VariantOps kVariant_ws_1024;  // warp-specialised pipeline (ws_kernel.cuh): 16-warp CTAs, two per SM
 
 }  // namespace dmel

@@ -168,6 +168,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -224,6 +227,132 @@ __device__ __forceinline__ void fft512_half_spectrum(float2 (&v)[16], float2 w1,
   for (int j = 0; j < 8; ++j)
     recv[j] = make_float2(__shfl_sync(0xffffffffu, send[j].x, partner), __shfl_sync(0xffffffffu, send[j].y, partner));
   unfold_half_spectrum(zlo, zhi, recv, base1024, out);
+}
+
+// ---- mel filterbank, log, quantise: the third phase of a tile ---------------------------------------------------
+// One lane per frame and PAIR of channels (m, m + 32/TF): a group of 2 * 32/TF adjacent channels side by side in a
+// warp.  The host pads the spans of a group to one common length and interleaves the weights of a pair step by step,
+// so the bin loop is warp-uniform and serves two independent accumulation chains; it also deals the groups to the
+// warps that run this phase (`slot` of `n_slots`) so that every one of them gets about the same number of steps.
+// `mags_sa` is the 32-bit shared address of the [frame][bin] magnitudes, rows kPitch floats apart.
+template <int TF, int MODE, int kPitch>
+__device__ __forceinline__ void mel_phase(const FusedParams& p, uint32_t sa_base, uint32_t mags_sa, int lane, int slot, int n_slots,
+                                          int cur_row, int cur_t0, int cur_valid, bool dead, unsigned long long& edge_hits) {
+  constexpr bool kCodes = (MODE & kOutCodes) != 0, kLogmel = (MODE & kOutLogmel) != 0;
+  constexpr bool kStats = (MODE & kOutStats) != 0, kEdge = (MODE & kOutEdge) != 0;
+  constexpr bool kBf16 = (MODE & kOutBf16) != 0, kDequant = (MODE & kOutDequant) != 0;
+  const int* s_order = reinterpret_cast<const int*>(__cvta_shared_to_generic(sa_base + p.off_order));
+  constexpr int kGroups = 32 / TF;
+  constexpr int kChanIter = 2 * kGroups;        // channels of a group
+  constexpr int kRecB = kGroups * (int)sizeof(ChanRec);  // record of the pair's second channel
+  const int fr = lane % TF;
+  const int sub = lane / TF;
+  const int t = cur_t0 + fr;
+  const size_t opair = (size_t)kGroups * p.n_frames;  // from a pair's first channel to its second
+  const size_t obase = (size_t)cur_row * p.n_mels * p.n_frames + t;
+  auto store_logmel = [&](size_t at, float v) {
+    if constexpr (kBf16) reinterpret_cast<__nv_bfloat16*>(p.logmel)[at] = __float2bfloat16_rn(v);
+    else p.logmel[at] = v;
+  };
+  if (dead) {
+    // nothing of this tile is valid audio: codes are the pad value, masked log-mel is zero
+    if constexpr (kCodes || kLogmel) {
+      const bool in_row = t < p.n_frames;
+#pragma unroll 1
+      for (int m = slot * kGroups + sub; m < p.n_mels; m += n_slots * kGroups) {
+        const size_t od = obase + (size_t)m * p.n_frames;
+        if (in_row) {
+          if constexpr (kCodes) p.codes[od] = 0;
+          if constexpr (kDequant) p.dequant[od] = 0.f;
+          if constexpr (kLogmel) store_logmel(od, 0.f);
+        }
+      }
+    }
+  } else {
+    const uint32_t xrow = mags_sa + (uint32_t)fr * (kPitch * 4);
+    const uint32_t wbase = sa_base + p.off_weights;
+    const uint32_t rec0 = sa_base + p.off_rec + (uint32_t)sub * (uint32_t)sizeof(ChanRec);
+    const bool in_row = t < p.n_frames;
+    const bool valid = t < cur_valid;
+    // everything that happens to one channel's value.  kFull: all TF frames of the tile are valid frames of
+    // the row and no phantom channel pads a group - the common case, whose epilogue carries no predicates.
+    auto emit = [&]<bool kFull>(std::bool_constant<kFull>, float value, const float4& q, uint32_t rec_at, int m, size_t at) {
+      const bool live = kFull || m < p.n_mels;
+      const bool ok = kFull || (live && in_row);
+      const bool val = kFull || valid;
+      if constexpr (kLogmel) {
+        const float out = (!kFull && p.mask_invalid && !val) ? 0.f : value;
+        if (ok) store_logmel(at, out);
+        if (p.row_sum) {  // per (row, channel) sum over time: the caller's mels.mean(-1) without another pass
+          float part = ok ? out : 0.f;
+#pragma unroll
+          for (int d = TF / 2; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+          if (fr == 0 && live) atomicAdd(p.row_sum + (size_t)cur_row * p.n_mels + m, part);
+        }
+      }
+      if constexpr (kCodes) {
+        const float pos = __fmul_rn(__fsub_rn(value, q.x), q.y);
+        const float qf = fminf(fmaxf(floorf(pos), 0.f), p.kmax);
+        if (ok) p.codes[at] = val ? (unsigned char)qf : (unsigned char)0;
+        if constexpr (kDequant) {  // the table entry the stand-alone decoder would look up, same two roundings
+          const float centre = __fadd_rn(q.x, __fmul_rn(qf + 0.5f, q.z));
+          if (ok) p.dequant[at] = val ? centre : 0.f;
+        }
+        if constexpr (kEdge) {
+          const float e = fminf(fmaxf(rintf(pos), 1.f), p.kmax);
+          if (live && val && fabsf(pos - e) < p.edge_eps * q.y) ++edge_hits;
+        }
+      }
+      if constexpr (kStats) {
+        float lo = (val && live) ? value : __int_as_float(0x7f800000);
+        float hi = (val && live) ? value : __int_as_float(0xff800000);
+#pragma unroll
+        for (int d = TF / 2; d >= 1; d >>= 1) {
+          lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+          hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+        }
+        if (fr == 0 && live) sts_f2(rec_at + 16, fminf(q.x, lo), fmaxf(q.y, hi));  // channel m always belongs to this lane of this warp: no race
+      }
+    };
+    auto sweep = [&](auto full_tag) {
+#pragma unroll 1
+      for (int k = slot; k < p.n_order; k += n_slots) {
+        const int g = s_order[k];
+        if (g < 0) continue;  // (warp-uniform)
+        const int m = g * kChanIter + sub;
+        const uint32_t rec = rec0 + (uint32_t)g * (kChanIter * (int)sizeof(ChanRec));
+        const size_t o = obase + (size_t)m * p.n_frames;
+        const int4 ca = lds_i4(rec), cb = lds_i4(rec + kRecB);
+        const float4 qa = lds_f4(rec + 16), qb = lds_f4(rec + kRecB + 16);
+        // banded dot products of this lane's frame with the two channels: same span length, weights interleaved
+        uint32_t wa = wbase + ca.y, xa = xrow + ca.x, xb = xrow + cb.x;
+        const uint32_t xe = xa + ca.z;
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 1
+        do {
+          const float4 wA = lds_f4(wa), wB = lds_f4(wa + 16);
+          const float4 xA = lds_f4(xa), xB = lds_f4(xb);
+          wa += 32;
+          xa += 16;
+          xb += 16;
+          a0 = fmaf(wA.x, xA.x, a0);
+          b0 = fmaf(wB.x, xB.x, b0);
+          a1 = fmaf(wA.y, xA.y, a1);
+          b1 = fmaf(wB.y, xB.y, b1);
+          a0 = fmaf(wA.z, xA.z, a0);
+          b0 = fmaf(wB.z, xB.z, b0);
+          a1 = fmaf(wA.w, xA.w, a1);
+          b1 = fmaf(wB.w, xB.w, b1);
+        } while (xa != xe);
+        const float va = fast_log(fmaxf(a0 + a1, kLogClip));
+        const float vb = fast_log(fmaxf(b0 + b1, kLogClip));
+        emit(full_tag, va, qa, rec, m, o);
+        emit(full_tag, vb, qb, rec + kRecB, m + kGroups, o + opair);
+      }
+    };
+    if ((cur_t0 + TF <= cur_valid) && (p.n_chan_pad == p.n_mels)) sweep(std::true_type{});
+    else sweep(std::false_type{});
+  }
 }
 
 // OCC = CTAs per SM the instantiation is built for.  OCC == 3 (n_fft 1024, TF 8 only) trades
@@ -680,123 +809,8 @@ __global__ void __launch_bounds__(kThreads, OCC) dmel_fused_kernel(const __grid_
     }
 
     // ---- 3. mel filterbank, log, quantise --------------------------------
-    // One lane per frame and PAIR of channels (m, m + 32/TF): a group of 2 * 32/TF adjacent channels side by
-    // side in a warp.  The host pads the spans of a group to one common length and interleaves the weights of
-    // a pair step by step, so the bin loop is warp-uniform and serves two independent accumulation chains; it
-    // also deals the groups to the warps so that every warp gets about the same number of steps.
-    if (!DMEL_SKIP(p, 2)) {
-      constexpr int kGroups = 32 / TF;
-      constexpr int kChanIter = 2 * kGroups;        // channels of a group
-      constexpr int kRecB = kGroups * (int)sizeof(ChanRec);  // record of the pair's second channel
-      const int fr = lane % TF;
-      const int sub = lane / TF;
-      const int t = cur_t0 + fr;
-      const size_t opair = (size_t)kGroups * p.n_frames;  // from a pair's first channel to its second
-      const size_t obase = (size_t)cur_row * p.n_mels * p.n_frames + t;
-      auto store_logmel = [&](size_t at, float v) {
-        if constexpr (kBf16) reinterpret_cast<__nv_bfloat16*>(p.logmel)[at] = __float2bfloat16_rn(v);
-        else p.logmel[at] = v;
-      };
-      if (dead) {
-        // nothing of this tile is valid audio: codes are the pad value, masked log-mel is zero
-        if constexpr (kCodes || kLogmel) {
-          const bool in_row = t < p.n_frames;
-#pragma unroll 1
-          for (int m = warp * kGroups + sub; m < p.n_mels; m += kWarps * kGroups) {
-            const size_t od = obase + (size_t)m * p.n_frames;
-            if (in_row) {
-              if constexpr (kCodes) p.codes[od] = 0;
-              if constexpr (kDequant) p.dequant[od] = 0.f;
-              if constexpr (kLogmel) store_logmel(od, 0.f);
-            }
-          }
-        }
-      } else {
-        const uint32_t xrow = sa_base + p.off_mags + (uint32_t)fr * (kPitch * 4);
-        const uint32_t wbase = sa_base + p.off_weights;
-        const uint32_t rec0 = sa_base + p.off_rec + (uint32_t)sub * (uint32_t)sizeof(ChanRec);
-        const bool in_row = t < p.n_frames;
-        const bool valid = t < cur_valid;
-        // everything that happens to one channel's value.  kFull: all TF frames of the tile are valid frames of
-        // the row and no phantom channel pads a group - the common case, whose epilogue carries no predicates.
-        auto emit = [&]<bool kFull>(std::bool_constant<kFull>, float value, const float4& q, uint32_t rec_at, int m, size_t at) {
-          const bool live = kFull || m < p.n_mels;
-          const bool ok = kFull || (live && in_row);
-          const bool val = kFull || valid;
-          if constexpr (kLogmel) {
-            const float out = (!kFull && p.mask_invalid && !val) ? 0.f : value;
-            if (ok) store_logmel(at, out);
-            if (p.row_sum) {  // per (row, channel) sum over time: the caller's mels.mean(-1) without another pass
-              float part = ok ? out : 0.f;
-#pragma unroll
-              for (int d = TF / 2; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-              if (fr == 0 && live) atomicAdd(p.row_sum + (size_t)cur_row * p.n_mels + m, part);
-            }
-          }
-          if constexpr (kCodes) {
-            const float pos = __fmul_rn(__fsub_rn(value, q.x), q.y);
-            const float qf = fminf(fmaxf(floorf(pos), 0.f), p.kmax);
-            if (ok) p.codes[at] = val ? (unsigned char)qf : (unsigned char)0;
-            if constexpr (kDequant) {  // the table entry the stand-alone decoder would look up, same two roundings
-              const float centre = __fadd_rn(q.x, __fmul_rn(qf + 0.5f, q.z));
-              if (ok) p.dequant[at] = val ? centre : 0.f;
-            }
-            if constexpr (kEdge) {
-              const float e = fminf(fmaxf(rintf(pos), 1.f), p.kmax);
-              if (live && val && fabsf(pos - e) < p.edge_eps * q.y) ++edge_hits;
-            }
-          }
-          if constexpr (kStats) {
-            float lo = (val && live) ? value : __int_as_float(0x7f800000);
-            float hi = (val && live) ? value : __int_as_float(0xff800000);
-#pragma unroll
-            for (int d = TF / 2; d >= 1; d >>= 1) {
-              lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-              hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, d));
-            }
-            if (fr == 0 && live) sts_f2(rec_at + 16, fminf(q.x, lo), fmaxf(q.y, hi));  // channel m always belongs to this lane of this warp: no race
-          }
-        };
-        auto sweep = [&](auto full_tag) {
-#pragma unroll 1
-          for (int k = warp; k < p.n_order; k += kWarps) {
-            const int g = s_order[k];
-            if (g < 0) continue;  // (warp-uniform)
-            const int m = g * kChanIter + sub;
-            const uint32_t rec = rec0 + (uint32_t)g * (kChanIter * (int)sizeof(ChanRec));
-            const size_t o = obase + (size_t)m * p.n_frames;
-            const int4 ca = lds_i4(rec), cb = lds_i4(rec + kRecB);
-            const float4 qa = lds_f4(rec + 16), qb = lds_f4(rec + kRecB + 16);
-            // banded dot products of this lane's frame with the two channels: same span length, weights interleaved
-            uint32_t wa = wbase + ca.y, xa = xrow + ca.x, xb = xrow + cb.x;
-            const uint32_t xe = xa + ca.z;
-            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll 1
-            do {
-              const float4 wA = lds_f4(wa), wB = lds_f4(wa + 16);
-              const float4 xA = lds_f4(xa), xB = lds_f4(xb);
-              wa += 32;
-              xa += 16;
-              xb += 16;
-              a0 = fmaf(wA.x, xA.x, a0);
-              b0 = fmaf(wB.x, xB.x, b0);
-              a1 = fmaf(wA.y, xA.y, a1);
-              b1 = fmaf(wB.y, xB.y, b1);
-              a0 = fmaf(wA.z, xA.z, a0);
-              b0 = fmaf(wB.z, xB.z, b0);
-              a1 = fmaf(wA.w, xA.w, a1);
-              b1 = fmaf(wB.w, xB.w, b1);
-            } while (xa != xe);
-            const float va = fast_log(fmaxf(a0 + a1, kLogClip));
-            const float vb = fast_log(fmaxf(b0 + b1, kLogClip));
-            emit(full_tag, va, qa, rec, m, o);
-            emit(full_tag, vb, qb, rec + kRecB, m + kGroups, o + opair);
-          }
-        };
-        if ((cur_t0 + TF <= cur_valid) && (p.n_chan_pad == p.n_mels)) sweep(std::true_type{});
-        else sweep(std::false_type{});
-      }
-    }
+    if (!DMEL_SKIP(p, 2))
+      mel_phase<TF, MODE, kPitch>(p, sa_base, sa_base + p.off_mags, lane, warp, kWarps, cur_row, cur_t0, cur_valid, dead, edge_hits);
     __syncthreads();  // magnitudes are free again; the slot describes the next tile
     const int4 nx0 = lds_i4(sa_slot), nx1 = lds_i4(sa_slot + 16);
     tile = nx0.x;
