@@ -61,6 +61,7 @@ struct dmel_plan {
   int sm_count = 0;
   int max_smem = 0;
   int n_fft = 0, hop = 0, n_mels = 0, center = 0;
+  int core_fft = 0;  // transform size of the kernel that runs it: 1024 for n_fft <= 1024, else 2048
   int pad_inner = 0, pad_outer = 0;
   int tile_frames = 0;  // TF chosen for this geometry
   int ctas_per_sm = 1;
@@ -334,8 +335,8 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
   if (!out) return fail(DMEL_ERR_INVALID, "out is null");
   *out = nullptr;
   if (!mel_basis_host || !window_host) return fail(DMEL_ERR_INVALID, "mel_basis_host / window_host is null");
-  if (n_fft != 1024 && n_fft != 2048)
-    return fail(DMEL_ERR_UNSUPPORTED, "n_fft=%d: this build has kernels for n_fft 1024 and 2048 only", n_fft);
+  if (n_fft < 64 || n_fft > 2048 || (n_fft & (n_fft - 1)) != 0)
+    return fail(DMEL_ERR_UNSUPPORTED, "n_fft=%d: this build has radix kernels for powers of two from 64 to 2048", n_fft);
   if (hop_length < 1 || hop_length > n_fft)
     return fail(DMEL_ERR_INVALID, "hop_length must be in [1, n_fft], got %d", hop_length);
   if (n_mels < 1 || n_mels > 1024) return fail(DMEL_ERR_INVALID, "n_mels must be in [1, 1024], got %d", n_mels);
@@ -372,17 +373,32 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
   const char* ws_env = std::getenv("DMEL_WS");
   const bool ws_on = ws_env ? std::atoi(ws_env) != 0 : false;  // off: it measured 115 us per step against 92.6 (profiles/history.md)
   (void)ws_on;
+  // A frame of n_fft < 1024 samples runs on the 1024-point kernel, zero-extended: X_n[k] of the short frame is bin
+  // k * (1024 / n_fft) of the long one, exactly (same sum, the added taps are zero).  So the window is embedded in
+  // the first n_fft taps and every filterbank weight moves to the bin it now lives at; geometry (reflect pad, frame
+  // count) keeps following the caller's n_fft.  The extra FFT work is the price of one kernel family.
+  const int core = n_fft > 1024 ? 2048 : 1024;
+  const int ratio = core / n_fft, core_freq = core / 2 + 1;
+  plan->core_fft = core;
+  std::vector<float> basis_core;
+  const float* basis = mel_basis_host;
+  if (ratio > 1) {
+    basis_core.assign((size_t)n_mels * core_freq, 0.f);
+    for (int m = 0; m < n_mels; ++m)
+      for (int k = 0; k <= n_fft / 2; ++k) basis_core[(size_t)m * core_freq + (size_t)k * ratio] = mel_basis_host[(size_t)m * (n_fft / 2 + 1) + k];
+    basis = basis_core.data();
+  }
   std::vector<int4> chan;
   std::vector<float> weights;
   std::vector<int> group_steps, order;
   for (const dmel::VariantOps* v : kVariants) {
-    if (v->n_fft != n_fft || (occ_pin && v->occ != occ_pin)) continue;
+    if (v->n_fft != core || (occ_pin && v->occ != occ_pin)) continue;
 #ifdef DMEL_WITH_WS
     if (v == &dmel::kVariant_ws_1024 && (occ_pin || !ws_on || center)) continue;
 #endif
-    band_filterbank(mel_basis_host, n_mels, n_fft / 2 + 1, 32 / v->tf, &chan, &weights, &group_steps);
+    band_filterbank(basis, n_mels, core_freq, 32 / v->tf, &chan, &weights, &group_steps);
     order = deal_groups(group_steps, v->mel_warps, v->mel_warps == dmel::kWarps);
-    const int wave_len = ((v->tf - 1) * hop_length + n_fft + 7) / 8 * 8;  // whole 16-byte units of float and of int16
+    const int wave_len = ((v->tf - 1) * hop_length + core + 7) / 8 * 8;  // whole 16-byte units of float and of int16
     const size_t need = v->smem_need(wave_len, (int)chan.size(), (int)weights.size(), (int)order.size());
     const size_t limit = std::min<size_t>((size_t)max_sm_smem / v->occ - 1024, (size_t)plan->max_smem);  // 1 KB/CTA reserved
     if (need <= limit) {
@@ -403,18 +419,19 @@ int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center, const fl
     return fail(DMEL_ERR_UNSUPPORTED, "geometry needs more than %d bytes of shared memory per CTA", max_smem);
   }
 
-  std::vector<float> window(window_host, window_host + n_fft);
-  // inter-pass twiddles W_C^{k1*n2} (C = n_fft/2 complex points, n2 = lane) and unfold twiddles W_{n_fft}^k
-  const int n_complex = n_fft / 2, rows = n_complex / 32;
-  std::vector<float2> stage_tw((size_t)rows * 32), fold_tw(n_fft / 4 + 1);
+  std::vector<float> window(core, 0.f);  // taps past n_fft stay zero (see above)
+  std::copy(window_host, window_host + n_fft, window.begin());
+  // inter-pass twiddles W_C^{k1*n2} (C = core/2 complex points, n2 = lane) and unfold twiddles W_{core}^k
+  const int n_complex = core / 2, rows = n_complex / 32;
+  std::vector<float2> stage_tw((size_t)rows * 32), fold_tw(core / 4 + 1);
   const double two_pi = 6.283185307179586476925286766559;
   for (int k1 = 0; k1 < rows; ++k1)
     for (int n2 = 0; n2 < 32; ++n2) {
       const double a = -two_pi * double((k1 * n2) % n_complex) / n_complex;
       stage_tw[k1 * 32 + n2] = make_float2((float)std::cos(a), (float)std::sin(a));
     }
-  for (int k = 0; k <= n_fft / 4; ++k) {
-    const double a = -two_pi * double(k) / n_fft;
+  for (int k = 0; k <= core / 4; ++k) {
+    const double a = -two_pi * double(k) / core;
     fold_tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
   }
   std::vector<float> window_pcm(window);
@@ -461,10 +478,10 @@ void dmel_plan_destroy(dmel_plan* plan) {
 int dmel_plan_describe(const dmel_plan* plan, char* buf, size_t buf_len) {
   if (!plan || !buf || buf_len == 0) return fail(DMEL_ERR_INVALID, "plan / buf is null");
   snprintf(buf, buf_len,
-           "{\"n_fft\": %d, \"hop\": %d, \"n_mels\": %d, \"center\": %d, \"tile_frames\": %d, "
+           "{\"n_fft\": %d, \"core_fft\": %d, \"hop\": %d, \"n_mels\": %d, \"center\": %d, \"tile_frames\": %d, "
            "\"ctas_per_sm\": %d, \"smem_bytes\": %zu, \"banded_weights\": %d, \"n_chan_pad\": %d, "
            "\"wave_len\": %d, \"sm_count\": %d}",
-           plan->n_fft, plan->hop, plan->n_mels, plan->center, plan->tile_frames, plan->ctas_per_sm,
+           plan->n_fft, plan->core_fft, plan->hop, plan->n_mels, plan->center, plan->tile_frames, plan->ctas_per_sm,
            plan->smem_bytes, plan->nnz, plan->n_chan_pad, plan->wave_len, plan->sm_count);
   return DMEL_OK;
 }

@@ -52,7 +52,9 @@ const char* dmel_last_error(void);
  *   mel_basis_host : (n_mels, n_fft/2+1) float32, row-major  (librosa.filters.mel, :45-52)
  *   window_host    : (n_fft) float32, already centre-padded if win_length < n_fft (:53)
  *   center         : 0/1, the `center` flag handed to torch.stft (:70)
- * The reflect pad (n_fft - hop)/2 of :58-62 is implied.  Supported n_fft: 1024, 2048.
+ * The reflect pad (n_fft - hop)/2 of :58-62 is implied.  Supported n_fft: powers of two from 64 to 2048 (1024 and
+ * 2048 have kernels of their own; a shorter frame runs zero-extended on the 1024-point kernel, which is exact);
+ * anything else returns DMEL_ERR_UNSUPPORTED.
  * The plan binds to the CUDA device that is current at the time of the call. */
 int dmel_plan_create(int n_fft, int hop_length, int n_mels, int center,
                      const float* mel_basis_host, const float* window_host,

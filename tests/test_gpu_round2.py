@@ -225,7 +225,7 @@ def test_minus_zero_and_nan_do_not_corrupt_the_statistics(d):
 def test_plan_creation_failure_paths_do_not_leak_or_wedge(d):
     from dmel_codec_b200 import _native
     with pytest.raises(NotImplementedError):  # no kernel for this n_fft
-        d.LogMelSpectrogram(sample_rate=16000, n_fft=4096, win_length=4096, hop_length=1024, n_mels=80)(torch.zeros(1, 8192, device="cuda"))
+        d.LogMelSpectrogram(sample_rate=16000, n_fft=4096, win_length=4096, hop_length=1024, n_mels=80)(torch.zeros(1, 16384, device="cuda"))
     with pytest.raises((ValueError, NotImplementedError, _native.DmelNativeError)):  # absurd channel count: no variant fits
         d.LogMelSpectrogram(sample_rate=16000, n_fft=1024, win_length=1024, hop_length=256, n_mels=4000)(torch.zeros(1, 8192, device="cuda"))
     for _ in range(50):  # failed (or oversized) creations leave nothing behind that a later plan trips over
@@ -393,3 +393,49 @@ def test_zero_copy_streaming_equals_offline(d):
         pos += size
     got.append(enc.flush())
     assert torch.equal(torch.cat(got, dim=2), want)
+
+
+# ---------------------------------------------------------------------------
+# n_fft below 1024: the short frame runs zero-extended on the 1024-point kernel (exact bin subsampling)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [
+    dict(sample_rate=16000, n_fft=512, win_length=512, hop_length=128, n_mels=80),
+    dict(sample_rate=16000, n_fft=512, win_length=400, hop_length=160, n_mels=64),    # the classic 25 ms / 10 ms speech front end
+    dict(sample_rate=8000, n_fft=256, win_length=256, hop_length=64, n_mels=40),
+    dict(sample_rate=22050, n_fft=512, win_length=512, hop_length=512, n_mels=80),    # no overlap
+    dict(sample_rate=16000, n_fft=128, win_length=128, hop_length=32, n_mels=20),
+    dict(sample_rate=16000, n_fft=512, win_length=512, hop_length=128, n_mels=80, center=True),
+], ids=["512_128", "512_win400_hop160", "256_64", "512_hop512", "128_32", "512_center"])
+def test_small_n_fft_against_the_oracle(d, kw):
+    from dmel_codec_b200 import synth
+    wav = synth.batch(range(500, 503), 20011, kw["sample_rate"], "speech")
+    ref = O.log_mel(wav, oracle_config(kw))
+    tr = _transform(d, kw)
+    got = tr(wav.cuda()).cpu()
+    assert got.shape == ref.shape
+    ok, ratio = logmel_close(got, ref, REL_TOL)
+    assert ok, f"{ratio:.2f}x tolerance"
+    info = tr.spectrogram.plan_for(torch.device("cuda", torch.cuda.current_device())).describe()
+    assert info["n_fft"] == kw["n_fft"] and info["core_fft"] == 1024
+    # and the quantiser path on top of it
+    lo, hi = O.calibrate_minmax(ref)
+    tok = _tokenizer(d, kw, 16)
+    tok.quantizer.set_stats(lo, hi)
+    codes, _ = tok.encode(wav.cuda())
+    _check_codes(codes, ref, lo, hi, 16)
+    # streaming over the short transform: same codes as offline
+    if not kw.get("center"):
+        enc = d.DMelStreamEncoder(tok, n_streams=3, capacity_samples=8192)
+        outs, pos = [], 0
+        while pos < wav.shape[2]:
+            outs.append(enc.push(wav[:, 0, pos:pos + 1000].cuda()))
+            pos += 1000
+        outs.append(enc.flush())
+        assert torch.equal(torch.cat(outs, dim=2), codes)
+
+
+def test_unsupported_n_fft_is_refused(d):
+    for n_fft in (400, 1000, 4096, 32):
+        with pytest.raises(NotImplementedError, match="n_fft"):
+            d.LogMelSpectrogram(sample_rate=16000, n_fft=n_fft, win_length=min(n_fft, 400), hop_length=100, n_mels=40)(
+                torch.zeros(1, 8000, device="cuda"))
