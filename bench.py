@@ -647,16 +647,26 @@ def standalone_kernels(dev):
     peak, _ = measured_peaks()
     n = b * m * t
     out = {}
+    from dmel_codec_b200 import FSQIndexer
+    fsq = FSQIndexer(levels=(7, 5, 5), groups=10)              # reference config/lm/lm_config.yaml:95-107
+    zb, zt = 64, 65536
+    zp = torch.randn((zb, zt, 10, 3), dtype=torch.float32, device=dev)
+    n_fsq = zb * zt * 10
+    gain_wav = torch.empty((64, 1 << 21), dtype=torch.float32, device=dev).uniform_(-0.5, 0.5)  # 512 MiB of waveform
+    plan = __import__("dmel_codec_b200").LogMelSpectrogram(sample_rate=16000, n_fft=1024, win_length=1024, hop_length=256,
+                                                          n_mels=80).spectrogram.plan_for(dev)
     for name, fn, nbytes in (
             ("quantize_kernel", lambda i: P.quantize(mel, lo, scale, 16), 5 * n),
             ("dequantize_kernel", lambda i: P.dequantize(codes, table), 5 * n),
-            ("tensor_minmax_kernel", lambda i: P.tensor_minmax(mel, None, run_min, run_max), 4 * n)):
+            ("tensor_minmax_kernel", lambda i: P.tensor_minmax(mel, None, run_min, run_max), 4 * n),
+            ("row_absmax_kernel (peak normalisation gain)", lambda i: plan.peak_gain(gain_wav), 4 * gain_wav.numel()),
+            ("fsq_encode_kernel (indices + lm ids)", lambda i: fsq.encode(zp, return_codes=False, lm_codebook_size=180), (12 + 16) * n_fsq)):
         for i in range(2):
             fn(i)
         ms = time_kernel_ms(fn, 7, stream)
         out[name] = {"avg_launch_ms": ms, "algorithmic_bytes_per_launch": nbytes, "achieved": nbytes / (ms / 1e3) / 1e9,
-                     "unit": "GB/s", "frac": nbytes / (ms / 1e3) / 1e9 / peak, "shape": [b, m, t]}
-    del mel, codes
+                     "unit": "GB/s", "frac": nbytes / (ms / 1e3) / 1e9 / peak}
+    del mel, codes, zp, gain_wav
     torch.cuda.empty_cache()
     return out
 

@@ -7,6 +7,8 @@ plus the dMel quantiser the reference's README describes but does not ship):
     DMelQuantizer, DMelResult                 log-mel <-> uint8 codes, calibration
     DMelTokenizer                             waveform -> codes (fused kernel)
     DMelStreamEncoder                         the same, chunk by chunk (bit-identical to offline)
+    FSQIndexer                                next to the path: the weight-free core of the reference's learned
+                                              quantiser (FSQ codes / indices / id_shift)
 
 Everything computes in hand-written sm_100a CUDA reached through the C ABI in
 ``include/dmel_b200.h``; importing the package is cheap, the first call loads
@@ -15,6 +17,7 @@ Everything computes in hand-written sm_100a CUDA reached through the C ABI in
 from .spectrogram import LinearSpectrogram, LogMelSpectrogram
 from .quantizer import DMelQuantizer, DMelResult, DMelTokenizer
 from .streaming import DMelStreamEncoder
+from .fsq import FSQIndexer
 
 __all__ = ["LinearSpectrogram", "LogMelSpectrogram", "DMelQuantizer", "DMelResult", "DMelTokenizer",
-           "DMelStreamEncoder"]
+           "DMelStreamEncoder", "FSQIndexer"]

@@ -21,6 +21,7 @@
 #include "logmel_kernel.cuh"
 #include "codec_kernels.cuh"
 #include "extras_kernels.cuh"
+#include "fsq_kernels.cuh"
 
 namespace {
 
@@ -1096,6 +1097,60 @@ int dmel_tensor_minmax_f32(const float* logmel_dev, long long n_rows, int n_mels
   const int blocks = (int)std::min<unsigned>((lines + 7) / 8, (unsigned)sm_count_of(dev) * 8u);
   DMEL_CUDA(launch_pdl(dmel::tensor_minmax_kernel, dim3(blocks), dim3(dmel::kStreamThreads), 0, (cudaStream_t)stream,
                        logmel_dev, n_valid_dev, min_dev, max_dev, lines, (unsigned)n_frames, (unsigned)n_mels));
+  return DMEL_OK;
+}
+
+static int fsq_levels(const int* levels, int n_levels, dmel::FsqLevels* lv) {
+  if (!levels || n_levels < 1 || n_levels > dmel::kFsqMaxDims)
+    return fail(DMEL_ERR_INVALID, "n_levels must be in [1, %d], got %d", dmel::kFsqMaxDims, n_levels);
+  long long basis = 1;
+  lv->n_dims = n_levels;
+  for (int k = 0; k < n_levels; ++k) {
+    if (levels[k] < 2 || levels[k] > 1024) return fail(DMEL_ERR_INVALID, "levels[%d] = %d outside [2, 1024]", k, levels[k]);
+    const float l = (float)levels[k];
+    lv->level[k] = levels[k];
+    lv->half_l[k] = (l - 1.f) * (1.f + 1e-3f) / 2.f;          // FSQ.bound, eps = 1e-3
+    lv->offset[k] = levels[k] % 2 == 0 ? 0.5f : 0.f;
+    lv->shift[k] = std::atanh(lv->offset[k] / lv->half_l[k]);
+    lv->half_width[k] = levels[k] / 2;
+    lv->basis[k] = (int)basis;
+    basis *= levels[k];
+    if (basis > 0x7fffffffLL) return fail(DMEL_ERR_INVALID, "codebook of %lld entries exceeds 2^31", basis);
+  }
+  return DMEL_OK;
+}
+
+int dmel_fsq_encode(const float* zp_dev, long long n_rows, long long n_steps, int n_groups, const int* levels,
+                    int n_levels, float* codes_dev, long long* indices_dev, long long* lm_ids_dev, int codebook_size,
+                    void* stream) {
+  dmel::FsqLevels lv;
+  int rc = fsq_levels(levels, n_levels, &lv);
+  if (rc != DMEL_OK) return rc;
+  if (!zp_dev) return fail(DMEL_ERR_INVALID, "zp_dev is null");
+  if (!codes_dev && !indices_dev && !lm_ids_dev) return fail(DMEL_ERR_INVALID, "no output requested");
+  if (n_rows < 0 || n_rows > 65535 || n_steps < 1 || n_steps > (1LL << 30) || n_groups < 1 || n_groups > 512)
+    return fail(DMEL_ERR_INVALID, "bad shape (%lld, %lld, %d)", n_rows, n_steps, n_groups);
+  if (n_rows == 0) return DMEL_OK;
+  DeviceGuard guard(device_of(zp_dev));
+  const dim3 grid((unsigned)((n_steps + dmel::kFsqTileT - 1) / dmel::kFsqTileT), (unsigned)n_rows);
+  DMEL_CUDA(launch_pdl(dmel::fsq_encode_kernel, grid, dim3(dmel::kFsqThreads), (size_t)dmel::kFsqTileT * n_groups * sizeof(long long),
+                       (cudaStream_t)stream, zp_dev, (int)n_steps, n_groups, lv, codes_dev, indices_dev, lm_ids_dev, codebook_size));
+  return DMEL_OK;
+}
+
+int dmel_fsq_decode(const long long* indices_dev, long long n_rows, long long n_steps, int n_groups, const int* levels,
+                    int n_levels, float* codes_dev, void* stream) {
+  dmel::FsqLevels lv;
+  int rc = fsq_levels(levels, n_levels, &lv);
+  if (rc != DMEL_OK) return rc;
+  if (!indices_dev || !codes_dev) return fail(DMEL_ERR_INVALID, "indices_dev / codes_dev is null");
+  if (n_rows < 0 || n_rows > 65535 || n_steps < 1 || n_steps > (1LL << 30) || n_groups < 1 || n_groups > 512)
+    return fail(DMEL_ERR_INVALID, "bad shape (%lld, %lld, %d)", n_rows, n_steps, n_groups);
+  if (n_rows == 0) return DMEL_OK;
+  DeviceGuard guard(device_of(indices_dev));
+  const dim3 grid((unsigned)((n_steps + dmel::kFsqTileT - 1) / dmel::kFsqTileT), (unsigned)n_rows);
+  DMEL_CUDA(launch_pdl(dmel::fsq_decode_kernel, grid, dim3(dmel::kFsqThreads), 0, (cudaStream_t)stream, indices_dev, (int)n_steps,
+                       n_groups, lv, codes_dev));
   return DMEL_OK;
 }
 

@@ -271,6 +271,23 @@ int dmel_dequantize_f32(const uint8_t* codes_dev, long long n_rows, int n_mels, 
 int dmel_tensor_minmax_f32(const float* logmel_dev, long long n_rows, int n_mels, long long n_frames,
                            const int32_t* n_valid_dev, float* min_dev, float* max_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Next to the path: the elementwise core of the reference's LEARNED quantiser.
+ * Finite scalar quantisation of the per-group latents to codes and indices, as GroupedResidualFSQ(levels,
+ * num_quantizers = 1, groups = G) of vector_quantize_pytorch computes them between its learned project_in and
+ * project_out (reference models/modules/dowmsample_fsq.py:39-44, :95, :130-137), and the language model's id_shift
+ * (models/modules/lm_process_input.py:301-313) fused into the same pass.
+ *   zp_dev      (B, T, G, D) float32, D = n_levels <= 8
+ *   codes_dev   (B, T, G, D) float32 in [-1, 1], or NULL
+ *   indices_dev (B, G, T) int64 in [0, prod(levels)): the layout DownsampleFiniteScalarQuantize.encode returns; or NULL
+ *   lm_ids_dev  (B, T, G) int64 = index + g * codebook_size, or NULL */
+int dmel_fsq_encode(const float* zp_dev, long long n_rows, long long n_steps, int n_groups, const int* levels,
+                    int n_levels, float* codes_dev, long long* indices_dev, long long* lm_ids_dev, int codebook_size,
+                    void* stream);
+/* indices (B, G, T) int64 -> codes (B, T, G, D): FSQ.indices_to_codes (the input of the learned project_out). */
+int dmel_fsq_decode(const long long* indices_dev, long long n_rows, long long n_steps, int n_groups, const int* levels,
+                    int n_levels, float* codes_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,7 +3,7 @@
 # then post-process here (no GPU needed) with profiles/postprocess.sh.  Follows /opt/skills/guides/B200_PROFILING.md:
 # the command runs once without ncu first, clocks are not touched, nothing printed under ncu is a bench value.
 set -e
-CMD="python bench.py --steps 5 --warmup 3 --skip-cpu --skip-e2e"
+CMD="python bench.py --steps 5 --warmup 3 --quick"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain.log 2>&1
 # 1. launch list: every launch of our kernels with its duration

@@ -56,7 +56,7 @@ def test_argument_errors_without_touching_a_device(native_lib):
     handle = ctypes.c_void_p()
     basis = np.zeros((80, 257), np.float32)
     window = np.ones(512, np.float32)
-    rc = native_lib.dmel_plan_create(512, 128, 80, 0, basis.ctypes.data_as(ctypes.c_void_p),
+    rc = native_lib.dmel_plan_create(400, 100, 80, 0, basis.ctypes.data_as(ctypes.c_void_p),  # not a power of two
                                      window.ctypes.data_as(ctypes.c_void_p), ctypes.byref(handle))
     assert rc == _native.ERR_UNSUPPORTED
     with pytest.raises(NotImplementedError):
@@ -67,6 +67,9 @@ def test_argument_errors_without_touching_a_device(native_lib):
     with pytest.raises(ValueError):
         _native.check(rc)
     assert native_lib.dmel_quantize_u8(None, 1, 80, 10, None, None, 16, None, None) == _native.ERR_INVALID
+    assert native_lib.dmel_run(None, None, None) == _native.ERR_INVALID
+    bad_levels = (ctypes.c_int * 3)(7, 1, 5)
+    assert native_lib.dmel_fsq_encode(None, 1, 10, 10, bad_levels, 3, None, None, None, 0, None) == _native.ERR_INVALID
 
 
 def test_modules_reject_cpu_tensors():
