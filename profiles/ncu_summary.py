@@ -26,8 +26,28 @@ def ncu_csv(report, page, extra=()):
     return list(csv.reader(io.StringIO(out)))
 
 
+def traffic(report):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fused launch, as the JSON bench.py cites in roofline.traffic"""
+    import json
+    rows = ncu_csv(report, "raw")
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    name_i = hdr.index("Kernel Name")
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in data:
+        if "dmel_fused_kernel" in r[name_i]:
+            rd = float(r[hdr.index("dram__bytes_read.sum")].replace(",", "")) * scale[units[hdr.index("dram__bytes_read.sum")]]
+            wr = float(r[hdr.index("dram__bytes_write.sum")].replace(",", "")) * scale[units[hdr.index("dram__bytes_write.sum")]]
+            print(json.dumps({"kernel": r[name_i][:80], "dram_bytes_read": int(rd), "dram_bytes_written": int(wr),
+                              "dram_bytes_per_launch": int(rd + wr),
+                              "source": "ncu --set full --clock-control none, one launch of the benchmark step (profiles/capture.sh); "
+                                        "not measured in the bench run. Writes still in L2 when the launch ends are not counted"}, indent=1))
+            return
+
+
 def main():
     report = sys.argv[1]
+    if len(sys.argv) > 2 and sys.argv[2] == "--traffic":
+        return traffic(report)
     frames = float(sys.argv[2]) if len(sys.argv) > 2 else None
     rows = ncu_csv(report, "raw")
     hdr, units, data = rows[0], rows[1], rows[2:]

@@ -1,9 +1,12 @@
 #!/bin/bash
 # Turns the reports written by profiles/capture.sh (merged back into gpurun_out/) into the committed summaries.
+#   bash profiles/postprocess.sh r2
 set -e
-R=${1:-r1}
+R=${1:-r2}
 python profiles/ncu_summary.py gpurun_out/prof_full.ncu-rep 59968 > profiles/${R}_encode_dequant_ncu_summary.txt
-python profiles/line_profile.py gpurun_out/prof_full.ncu-rep dmel_codec_b200/libdmel_b200.so ILi1024ELi8ELi65ELi3E 59968 \
+# the library holds one cubin per translation unit: the line profile reads the variant's object file
+python profiles/line_profile.py gpurun_out/prof_full.ncu-rep dmel_codec_b200/_obj/libdmel_b200/fused_1024_8_3.o ILi1024ELi8ELi65ELi3E 59968 \
     > profiles/${R}_encode_line_profile.txt
-echo "launch list: filter gpurun_out/launches.csv to kernel, grid, block, gpu__time_duration (ns -> us) -> profiles/${R}_launches.csv"
-echo "traffic: dram__bytes_read.sum + dram__bytes_write.sum of the fused launch in the summary -> profiles/encode_traffic.json"
+python profiles/launch_list.py gpurun_out/launches.csv > profiles/${R}_launches.csv
+python profiles/pm_timeline.py gpurun_out/prof_pm.ncu-rep > profiles/${R}_encode_pm_timeline.txt || true
+python profiles/ncu_summary.py gpurun_out/prof_full.ncu-rep --traffic > profiles/encode_traffic.json
