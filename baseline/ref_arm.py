@@ -34,7 +34,7 @@ def available() -> bool:
 
 def install(force: bool = False) -> str:
     """Install the reference package into baseline/_ref (no-op when it is already there or the sources are absent)."""
-    if available() and not force:
+    if available() and not force and os.path.isdir(os.path.join(REF_DIR, "dmel_codec", "models", "modules", "bigvgan")):
         return "present"
     if not os.path.isdir(REF_SRC):
         return "reference sources absent (GPU box): using what travelled with the snapshot"
@@ -46,7 +46,27 @@ def install(force: bool = False) -> str:
         res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0 or not available():
         return f"pip install failed ({res.returncode}): {res.stderr.strip()[-300:]}"
+    # The reference's setup.py finds packages by __init__.py, and models/modules/bigvgan has none: pip leaves the vocoder
+    # (and with it the anti-aliased activation, torch path and CUDA sources) out.  Complete the install from the sources.
+    extra = os.path.join("dmel_codec", "models", "modules", "bigvgan")
+    dst = os.path.join(REF_DIR, extra)
+    if not os.path.isdir(dst):
+        shutil.copytree(os.path.join(REF_SRC, extra), dst, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
     return "installed"
+
+
+def load_activation():
+    """The reference's anti-aliased activation, torch path: (Activation1d class, activations module), imported
+    unmodified from baseline/_ref (namespace packages: the vocoder directory has no __init__.py)."""
+    path = os.path.join(REF_DIR, "dmel_codec", "models", "modules", "bigvgan", "alias_free_activation", "torch", "act.py")
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} not found: run __graft_entry__.build() where /root/reference exists")
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import importlib
+    act = importlib.import_module("dmel_codec.models.modules.bigvgan.alias_free_activation.torch.act")
+    activations = importlib.import_module("dmel_codec.models.modules.bigvgan.activations")
+    return act.Activation1d, activations
 
 
 def load(mel_fn):

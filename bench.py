@@ -668,7 +668,47 @@ def standalone_kernels(dev):
                      "unit": "GB/s", "frac": nbytes / (ms / 1e3) / 1e9 / peak}
     del mel, codes, zp, gain_wav
     torch.cuda.empty_cache()
+    out["antialias_snake_kernel"] = activation_entry(dev, peak)
     return out
+
+
+def activation_entry(dev, peak):
+    """BigVGAN's anti-aliased Snake activation: this library's one-pass kernel against the reference's
+    own torch path (UpSample1d -> SnakeBeta -> DownSample1d) on the same GPU; 4 bytes in + 4 bytes out per sample."""
+    import dmel_codec_b200 as d
+    b, c, t = 8, 256, 32768
+    x = torch.randn((b, c, t), dtype=torch.float32, device=dev)
+    mod = d.AntiAliasSnake(c).to(dev)
+    mod.alpha.normal_(0.0, 0.5)
+    mod.beta.normal_(0.0, 0.5)
+    y = torch.empty_like(x)
+    stream = torch.cuda.current_stream(dev)
+    for _ in range(2):
+        mod(x, out=y)
+    ms = time_kernel_ms(lambda i: mod(x, out=y), 7, stream)
+    nbytes = 8 * x.numel()
+    entry = {"avg_launch_ms": ms, "algorithmic_bytes_per_launch": nbytes, "achieved": nbytes / (ms / 1e3) / 1e9, "unit": "GB/s",
+             "frac": nbytes / (ms / 1e3) / 1e9 / peak, "shape": [b, c, t]}
+    try:
+        from baseline import ref_arm
+        Activation1d, activations = ref_arm.load_activation()
+        act = activations.SnakeBeta(c, alpha_logscale=True).to(dev)
+        with torch.no_grad():
+            act.alpha.copy_(mod.alpha)
+            act.beta.copy_(mod.beta)
+            ref = Activation1d(activation=act).to(dev)
+            for _ in range(2):
+                want = ref(x)
+            ref_ms = time_kernel_ms(lambda i: ref(x), 5, stream)
+        err = ((y - want).abs() / want.abs().clamp(min=1.0)).max().item()
+        entry["reference_torch_path"] = {"avg_ms": ref_ms, "speedup": ref_ms / ms, "max_rel_err_vs_it": err,
+                                         "what": "reference Activation1d(SnakeBeta) from baseline/_ref, unmodified, CUDA tensors, same GPU. "
+                                                 "The reference's fused kernel is built for sm_70 / sm_80 without PTX and cannot run here"}
+    except Exception as e:  # baseline/_ref absent
+        entry["reference_torch_path"] = {"unavailable": str(e)[:200]}
+    del x, y
+    torch.cuda.empty_cache()
+    return entry
 
 
 def run_stream(args):

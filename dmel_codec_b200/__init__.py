@@ -9,6 +9,7 @@ plus the dMel quantiser the reference's README describes but does not ship):
     DMelStreamEncoder                         the same, chunk by chunk (bit-identical to offline)
     FSQIndexer                                next to the path: the weight-free core of the reference's learned
                                               quantiser (FSQ codes / indices / id_shift)
+    AntiAliasSnake                            next to the path: BigVGAN's anti-aliased Snake activation, one kernel
 
 Everything computes in hand-written sm_100a CUDA reached through the C ABI in
 ``include/dmel_b200.h``; importing the package is cheap, the first call loads
@@ -18,6 +19,7 @@ from .spectrogram import LinearSpectrogram, LogMelSpectrogram
 from .quantizer import DMelQuantizer, DMelResult, DMelTokenizer
 from .streaming import DMelStreamEncoder
 from .fsq import FSQIndexer
+from .activation import AntiAliasSnake
 
 __all__ = ["LinearSpectrogram", "LogMelSpectrogram", "DMelQuantizer", "DMelResult", "DMelTokenizer",
-           "DMelStreamEncoder", "FSQIndexer"]
+           "DMelStreamEncoder", "FSQIndexer", "AntiAliasSnake"]

@@ -76,6 +76,8 @@ SIGNATURES = {
     "dmel_fsq_encode": (c_int, [c_void_p, c_longlong, c_longlong, c_int, POINTER(c_int), c_int, c_void_p, c_void_p, c_void_p,
                                 c_int, c_void_p]),
     "dmel_fsq_decode": (c_int, [c_void_p, c_longlong, c_longlong, c_int, POINTER(c_int), c_int, c_void_p, c_void_p]),
+    "dmel_antialias_snake_f32": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]),
     "dmel_quantize_u8": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p]),
     "dmel_dequantize_f32": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_int, c_void_p,

@@ -25,7 +25,7 @@ OBJ_DIR = os.path.join(HERE, "_obj", os.path.splitext(os.path.basename(OUT))[0])
 VARIANTS = [(1024, 8, 3), (1024, 16, 2), (1024, 8, 2), (1024, 16, 1), (1024, 8, 1),
             (2048, 8, 2), (2048, 16, 1), (2048, 8, 1)]
 DEPS = ["dmel_b200.cu", "fused_variant.cu", "fused_ws_variant.cu", "ws_kernel.cuh", "fused_variants.h", "launch_util.cuh", "logmel_kernel.cuh",
-        "fft_core.cuh", "fastdiv.cuh", "codec_kernels.cuh", "extras_kernels.cuh", "fsq_kernels.cuh",
+        "fft_core.cuh", "fastdiv.cuh", "codec_kernels.cuh", "extras_kernels.cuh", "fsq_kernels.cuh", "activation_kernels.cuh",
         os.path.join("..", "..", "include", "dmel_b200.h")]
 NVCC_FLAGS = ["-std=c++20", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]

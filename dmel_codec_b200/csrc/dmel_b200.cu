@@ -22,6 +22,7 @@
 #include "codec_kernels.cuh"
 #include "extras_kernels.cuh"
 #include "fsq_kernels.cuh"
+#include "activation_kernels.cuh"
 
 namespace {
 
@@ -1151,6 +1152,27 @@ int dmel_fsq_decode(const long long* indices_dev, long long n_rows, long long n_
   const dim3 grid((unsigned)((n_steps + dmel::kFsqTileT - 1) / dmel::kFsqTileT), (unsigned)n_rows);
   DMEL_CUDA(launch_pdl(dmel::fsq_decode_kernel, grid, dim3(dmel::kFsqThreads), 0, (cudaStream_t)stream, indices_dev, (int)n_steps,
                        n_groups, lv, codes_dev));
+  return DMEL_OK;
+}
+
+int dmel_antialias_snake_f32(const float* x_dev, long long n_rows, int n_channels, long long n_steps, const float* up_taps_host,
+                             const float* down_taps_host, const float* log_alpha_dev, const float* log_beta_dev, float* y_dev,
+                             void* stream) {
+  if (!x_dev || !y_dev || !up_taps_host || !down_taps_host || !log_alpha_dev || !log_beta_dev)
+    return fail(DMEL_ERR_INVALID, "null pointer argument");
+  if (n_rows < 0 || n_rows > 65535 || n_channels < 1 || n_channels > 65535 || n_steps < 1 || n_steps > (1LL << 30))
+    return fail(DMEL_ERR_INVALID, "bad shape (%lld, %d, %lld)", n_rows, n_channels, n_steps);
+  if (n_rows == 0) return DMEL_OK;
+  dmel::ActTaps taps;
+  for (int k = 0; k < 12; ++k) {
+    if (!std::isfinite(up_taps_host[k]) || !std::isfinite(down_taps_host[k])) return fail(DMEL_ERR_INVALID, "filter tap %d is not finite", k);
+    taps.up2[k] = 2.0f * up_taps_host[k];  // the x2 of UpSample1d.forward (resample.py:31), exact
+    taps.down[k] = down_taps_host[k];
+  }
+  DeviceGuard guard(device_of(x_dev));
+  const dim3 grid((unsigned)((n_steps + dmel::kActTile - 1) / dmel::kActTile), (unsigned)n_channels, (unsigned)n_rows);
+  DMEL_CUDA(launch_pdl(dmel::antialias_snake_kernel, grid, dim3(dmel::kActThreads), 0, (cudaStream_t)stream, x_dev, y_dev, (int)n_steps,
+                       log_alpha_dev, log_beta_dev, taps));
   return DMEL_OK;
 }
 

@@ -288,6 +288,17 @@ int dmel_fsq_encode(const float* zp_dev, long long n_rows, long long n_steps, in
 int dmel_fsq_decode(const long long* indices_dev, long long n_rows, long long n_steps, int n_groups, const int* levels,
                     int n_levels, float* codes_dev, void* stream);
 
+/* BigVGAN's anti-aliased Snake activation, one pass: 2x upsample (12-tap FIR, replicate padding) -> x + sin^2(a x) / (b + 1e-9)
+ * -> 2x downsample (12-tap FIR, replicate padding).  Replaces Activation1d.forward of the reference
+ * (models/modules/bigvgan/alias_free_activation/torch/act.py:24-29, resample.py:10-58, activations.py:101-111) and its fused
+ * kernel for sm_70 / sm_80 (.../cuda/anti_alias_activation_cuda.cu:44-179), whose interface this mirrors: filters as the
+ * modules hold them (12 taps each, host arrays), alpha and beta per channel in LOG scale (device arrays; pass the same array
+ * twice for the one-parameter Snake).
+ *   x_dev, y_dev : (B, C, T) float32 */
+int dmel_antialias_snake_f32(const float* x_dev, long long n_rows, int n_channels, long long n_steps, const float* up_taps_host,
+                             const float* down_taps_host, const float* log_alpha_dev, const float* log_beta_dev, float* y_dev,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif
