@@ -58,7 +58,7 @@ def main():
         a[0] += int(r[ci]); a[1] += int(r[si]); a[2] += int(r[wi] or 0); a[3] += int(r[wx] or 0)
     total = sum(a[0] for a in agg.values())
     print(f"{'file:line':32s} {'inst/frame':>10s} {'%':>6s} {'samples':>8s} {'smem wf/frame':>14s} {'excess':>8s}")
-    for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
+    for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get("LP_LINES", "45"))]:
         name = f"{loc[0]}:{loc[1]}" if loc else "?"
         print(f"{name:32s} {a[0] / frames:10.1f} {100 * a[0] / total:6.1f} {a[1]:8d} {a[2] / frames:14.1f} {a[3] / frames:8.1f}")
 
