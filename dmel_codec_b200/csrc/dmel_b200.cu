@@ -580,6 +580,7 @@ int dmel_logmel_minmax_f32(dmel_plan* plan, const float* wav_dev, long long n_ro
   if (n_rows == 0) return DMEL_OK;
   p.lengths = lengths_dev;
   p.logmel = logmel_dev;
+  p.mask_invalid = lengths_dev != nullptr;  // frames past a row's length are written as 0 and never computed
   p.run_min = min_dev;
   p.run_max = max_dev;
   DeviceGuard guard(plan->device);

@@ -97,8 +97,9 @@ int dmel_minmax_f32(dmel_plan* plan, const float* wav_dev, long long n_rows, lon
                     long long row_stride, const int32_t* lengths_dev,
                     float* min_dev, float* max_dev, void* stream);
 
-/* dmel_logmel_f32 and dmel_minmax_f32 in one launch: writes the log-mel of every frame and folds the
- * valid ones into the running per-channel min / max.  With the log-mel of a shard kept in HBM the
+/* dmel_logmel_f32 and dmel_minmax_f32 in one launch: writes the log-mel of every valid frame (frames at or past
+ * lengths[b] / hop are written as 0 and never computed, as in dmel_logmel_masked; all frames when lengths_dev is
+ * NULL) and folds them into the running per-channel min / max.  With the log-mel of a shard kept in HBM the
  * calibrate-then-encode job of a dataset needs the STFT only once: pass 2 is dmel_quantize_u8 over the
  * stored tensor (bit-identical to the fused encode, which quantises the same float32 values). */
 int dmel_logmel_minmax_f32(dmel_plan* plan, const float* wav_dev, long long n_rows, long long n_samples,
