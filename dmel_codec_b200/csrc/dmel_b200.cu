@@ -1134,9 +1134,10 @@ int dmel_fsq_encode(const float* zp_dev, long long n_rows, long long n_steps, in
     return fail(DMEL_ERR_INVALID, "bad shape (%lld, %lld, %d)", n_rows, n_steps, n_groups);
   if (n_rows == 0) return DMEL_OK;
   DeviceGuard guard(device_of(zp_dev));
-  const dim3 grid((unsigned)((n_steps + dmel::kFsqTileT - 1) / dmel::kFsqTileT), (unsigned)n_rows);
-  DMEL_CUDA(launch_pdl(dmel::fsq_encode_kernel, grid, dim3(dmel::kFsqThreads), (size_t)dmel::kFsqTileT * n_groups * sizeof(long long),
-                       (cudaStream_t)stream, zp_dev, (int)n_steps, n_groups, lv, codes_dev, indices_dev, lm_ids_dev, codebook_size));
+  const int tile_t = std::max(8, std::min(dmel::kFsqTileT, (40 * 1024) / (n_groups * (int)sizeof(long long))));  // indices of a tile <= 40 KB
+  const dim3 grid((unsigned)((n_steps + tile_t - 1) / tile_t), (unsigned)n_rows);
+  DMEL_CUDA(launch_pdl(dmel::fsq_encode_kernel, grid, dim3(dmel::kFsqThreads), (size_t)tile_t * n_groups * sizeof(long long),
+                       (cudaStream_t)stream, zp_dev, (int)n_steps, n_groups, lv, codes_dev, indices_dev, lm_ids_dev, codebook_size, tile_t));
   return DMEL_OK;
 }
 
@@ -1152,7 +1153,7 @@ int dmel_fsq_decode(const long long* indices_dev, long long n_rows, long long n_
   DeviceGuard guard(device_of(indices_dev));
   const dim3 grid((unsigned)((n_steps + dmel::kFsqTileT - 1) / dmel::kFsqTileT), (unsigned)n_rows);
   DMEL_CUDA(launch_pdl(dmel::fsq_decode_kernel, grid, dim3(dmel::kFsqThreads), 0, (cudaStream_t)stream, indices_dev, (int)n_steps,
-                       n_groups, lv, codes_dev));
+                       n_groups, lv, codes_dev, dmel::kFsqTileT));
   return DMEL_OK;
 }
 

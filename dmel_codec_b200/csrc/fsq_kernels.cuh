@@ -17,7 +17,7 @@
 namespace dmel {
 
 constexpr int kFsqMaxDims = 8;
-constexpr int kFsqTileT = 64;
+constexpr int kFsqTileT = 256;  // time steps per CTA (the host lowers it when G is large: the tile's indices live in shared memory)
 constexpr int kFsqThreads = 256;
 
 struct FsqLevels {
@@ -26,15 +26,15 @@ struct FsqLevels {
   int half_width[kFsqMaxDims], basis[kFsqMaxDims], level[kFsqMaxDims];
 };
 
-// grid: (ceil(T / kFsqTileT), B); dynamic smem: kFsqTileT * G * 8 bytes (the tile's indices)
+// grid: (ceil(T / tile_t), B); dynamic smem: tile_t * G * 8 bytes (the tile's indices)
 __global__ void __launch_bounds__(kFsqThreads) fsq_encode_kernel(const float* __restrict__ zp, int n_t, int n_groups, FsqLevels lv,
                                                                  float* __restrict__ codes, long long* __restrict__ indices,
-                                                                 long long* __restrict__ lm_ids, int codebook_size) {
+                                                                 long long* __restrict__ lm_ids, int codebook_size, int tile_t) {
   extern __shared__ long long s_index[];  // [t in tile][g]
   grid_dependency_wait();
   grid_launch_dependents();
-  const int b = blockIdx.y, t0 = blockIdx.x * kFsqTileT;
-  const int nt = min(kFsqTileT, n_t - t0);
+  const int b = blockIdx.y, t0 = blockIdx.x * tile_t;
+  const int nt = min(tile_t, n_t - t0);
   const int d = lv.n_dims;
   const size_t base = ((size_t)b * n_t + t0) * n_groups;  // first (t, g) pair of the tile
   for (int i = threadIdx.x; i < nt * n_groups; i += kFsqThreads) {  // i = t * G + g: contiguous in zp
@@ -61,11 +61,11 @@ __global__ void __launch_bounds__(kFsqThreads) fsq_encode_kernel(const float* __
 
 // indices (B, G, T) int64 -> codes (B, T, G, D) float32 (FSQ.indices_to_codes without the learned project_out)
 __global__ void __launch_bounds__(kFsqThreads) fsq_decode_kernel(const long long* __restrict__ indices, int n_t, int n_groups, FsqLevels lv,
-                                                                 float* __restrict__ codes) {
+                                                                 float* __restrict__ codes, int tile_t) {
   grid_dependency_wait();
   grid_launch_dependents();
-  const int b = blockIdx.y, t0 = blockIdx.x * kFsqTileT;
-  const int nt = min(kFsqTileT, n_t - t0);
+  const int b = blockIdx.y, t0 = blockIdx.x * tile_t;
+  const int nt = min(tile_t, n_t - t0);
   const int d = lv.n_dims;
   for (int i = threadIdx.x; i < nt * n_groups; i += kFsqThreads) {
     const int t = i / n_groups, g = i - t * n_groups;
