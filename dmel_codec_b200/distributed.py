@@ -117,5 +117,7 @@ def _shard_logmel_fits(tokenizer, ids: Sequence[int], load_batch, batch_size: in
         return True
     frames = audios.shape[-1] // tokenizer.hop_length
     need = 4 * len(ids) * tokenizer.quantizer.n_mels * frames
+    if need <= (1 << 30) * KEEP_MEL_HBM_FRACTION and KEEP_MEL_HBM_FRACTION > 0:
+        return True  # under a GiB: not worth a driver query on a 180 GB part
     free, _total = torch.cuda.mem_get_info(audios.device)
     return need <= KEEP_MEL_HBM_FRACTION * free
