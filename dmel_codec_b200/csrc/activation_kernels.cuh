@@ -5,151 +5,183 @@
 // UpSample1d -> SnakeBeta -> DownSample1d, each a full HBM round trip of a tensor twice the size) and its fused
 // sm_70/sm_80 kernel (.../cuda/anti_alias_activation_cuda.cu:44-179, shipped without PTX: it cannot run on sm_100).
 //
-// One CTA = 1008 consecutive outputs of one (batch, channel) row:
-//   1. x[t0 - 8, t0 + 1016) -> shared (one LDG.128 per thread; row ends read through a clamped index, which IS the
-//      replicate padding of the upsampler);
-//   2. each thread produces 8 samples of the activated 2x signal s (4 even, 4 odd) from 12 x values held in registers
-//      (3 LDS.128): u[2m] = sum_q x[m-3+q] F[11-2q], u[2m+1] = sum_q x[m-2+q] F[10-2q] (F = 2 * up taps: the polyphase
-//      form of the transposed convolution), then the Snake with sin^2 evaluated on an argument reduced modulo pi
-//      (sin^2 has period pi: two-constant Cody-Waite + MUFU.SIN stays within 1e-6 of the exact value for the
-//      arguments a trained alpha produces); s is stored de-interleaved (even / odd) so that
-//   3. each thread computes 4 outputs from 6 LDS.128: y[t] = sum_a G[2a+1] s_even[..] + G[2a] s_odd[..].
-// Samples of s before the start / past the end of the row (the downsampler's replicate padding) are patched in shared
-// memory between steps 2 and 3.  HBM traffic: 4 bytes in, 4 bytes out per sample; ~46 instructions per output.
+// One WARP = 240 consecutive outputs of one (batch, channel) row, no shared memory and no barrier.  The op is bound
+// by the FP32 pipe, not by HBM: two 12-tap FIRs and the Snake are >= 40 FMA-pipe lane-cycles per output, which at
+// 128 lanes per SM and cycle is the same rate as the HBM roofline (8 bytes per output), and every lane-cycle spent
+// on anything else comes straight out of the throughput (profiles/r2_activation_ncu_summary.txt).
+//   1. lane l loads x[t0 - 8 + 8l .. + 8) with two LDG.128 (row ends through a clamped index, which IS the replicate
+//      padding of the upsampler) and fetches the eight samples that follow from lane l+1 (8 SHFL);
+//   2. it produces 8 PAIRS P[i] = (s[2 t0 - 5 + 2i], s[2 t0 - 4 + 2i]), i = 8l .. 8l+7, of the activated 2x signal s.
+//      Both halves of a pair are polyphase sums over the SAME six inputs,
+//        u_odd = sum_q x[t0 - 5 + i + q] F[10 - 2q],   u_even = sum_q x[t0 - 5 + i + q] F[11 - 2q]   (F = 2 * up taps),
+//      so one packed FMA (fma.rn.f32x2, the input broadcast to both halves) advances both; the Snake runs packed as
+//      well, with sin^2 evaluated on an argument reduced modulo pi (sin^2 has period pi: round-by-magic-constant,
+//      two-constant Cody-Waite and MUFU.SIN stay within 1e-6 of the exact value for the arguments a trained alpha
+//      produces).  Pairs that stand for samples of s before the start / past the end of the row (the downsampler's
+//      replicate padding) are overwritten in registers;
+//   3. it fetches the five pairs that follow from lane l+1 (10 SHFL) and computes 8 outputs,
+//      y[t0 + r] = sum_a P[r + a] . (G[2a], G[2a+1]): six packed FMAs and one add per output, two STG.128.
+// Lane 31 of step 2 and lanes 30-31 of step 3 have no complete neighbourhood and produce nothing: a warp reads 256
+// samples (L2 serves the 16 that overlap the next warp's) to write 240.  The grid is persistent (warps stride over
+// the tiles, the next tile's samples are in flight while this one is computed): benchmarks/stream_read.cu measures
+// what one short-lived block per tile costs on this part.  HBM traffic: 4 bytes in, 4 bytes out per sample.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "fastdiv.cuh"
+#include "fft_core.cuh"  // packed f32x2 arithmetic
+
 namespace dmel {
 
 constexpr int kActThreads = 256;
-constexpr int kActTile = 1008;            // outputs per CTA (a multiple of 4)
-constexpr int kActX = kActTile + 16;      // staged inputs: x[t0 - 8 .. t0 + kActTile + 8)
-constexpr int kActS = kActTile + 8;       // entries of s_even / s_odd: s[2 t0 - 6 + 2 i], s[2 t0 - 5 + 2 i]
+#ifndef DMEL_ACT_MIN_CTAS
+#define DMEL_ACT_MIN_CTAS 3  // register budget of the tile body: 80 (measured against 2 and 4 CTAs per SM, profiles/history.md)
+#endif
+constexpr int kActPer = 8;                // outputs per lane
+constexpr int kActWarpOut = 30 * kActPer;  // outputs per warp and tile
 
 struct ActTaps {
   float up2[12];   // 2 * up-sampling taps
   float down[12];
 };
 
-__device__ __forceinline__ float snake_value(float u, float a, float inv_b) {
-  const float v = u * a;
-  const float k = rintf(v * 0.31830988618379067f);                 // v / pi
-  float r = fmaf(-k, 3.140625f, v);                                 // pi = 3.140625 + 9.6765358979e-4 (Cody-Waite)
-  r = fmaf(-k, 9.67653589793e-4f, r);
-  const float sn = __sinf(r);
-  return fmaf(inv_b, sn * sn, u);
+// x + sin^2(a x) / b on both halves of a pair
+__device__ __forceinline__ float2 snake_pair(float2 u, float a, float inv_b) {
+  const float2 v = f2_mul(u, make_float2(a, a));
+  constexpr float kMagic = 12582912.f;  // 1.5 * 2^23: adding it rounds to the nearest integer (|v / pi| < 2^22)
+  const float2 k = f2_add(f2_fma(v, make_float2(0.31830988618379067f, 0.31830988618379067f), make_float2(kMagic, kMagic)),
+                          make_float2(-kMagic, -kMagic));
+  float2 r = f2_fma(k, make_float2(-3.140625f, -3.140625f), v);                 // pi = 3.140625 + 9.6765358979e-4 (Cody-Waite)
+  r = f2_fma(k, make_float2(-9.67653589793e-4f, -9.67653589793e-4f), r);
+  const float2 sn = make_float2(__sinf(r.x), __sinf(r.y));
+  return f2_fma(make_float2(inv_b, inv_b), f2_mul(sn, sn), u);
 }
 
-// grid (ceil(T / kActTile), C, B)
-__global__ void __launch_bounds__(kActThreads) antialias_snake_kernel(const float* __restrict__ x, float* __restrict__ y, int n_t,
+// four consecutive samples of one row from index g0 on, indices clamped into the row
+__device__ __forceinline__ float4 act_load(const float* __restrict__ xr, int g0, int n_t, bool row_vec) {
+  if (row_vec && g0 >= 0 && g0 + 3 < n_t) return __ldg(reinterpret_cast<const float4*>(xr + g0));
+  float4 v;
+  v.x = __ldg(xr + min(max(g0, 0), n_t - 1));
+  v.y = __ldg(xr + min(max(g0 + 1, 0), n_t - 1));
+  v.z = __ldg(xr + min(max(g0 + 2, 0), n_t - 1));
+  v.w = __ldg(xr + min(max(g0 + 3, 0), n_t - 1));
+  return v;
+}
+
+// One warp tile: 240 outputs from the 256 samples in (cur0, cur1) of every lane.  kEdge = the tile touches an end of
+// its row (replicate padding of the downsampler, partial stores); interior tiles are compiled without any of it -
+// as one body, the conditional overwrites of the pairs cost 45 register moves per tile on the pipe that binds.
+template <bool kEdge>
+__device__ __forceinline__ void act_tile(float4 cur0, float4 cur1, int lane, int t0, int n_t, float a, float inv_b,
+                                         const ActTaps& taps, float* __restrict__ yrow, bool vec_st) {
+  // ---- 1. w[j] = x[t0 - 8 + 8 lane + j], j = 0 .. 15
+  float w[16] = {cur0.x, cur0.y, cur0.z, cur0.w, cur1.x, cur1.y, cur1.z, cur1.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) w[8 + j] = __shfl_down_sync(0xffffffffu, w[j], 1);
+  // ---- 2. pairs 8 lane .. 8 lane + 7;  x[t0 - 5 + i + q] = w[d + 3 + q]
+  float2 pv[kActPer + 5];
+#pragma unroll
+  for (int d = 0; d < kActPer; ++d) {
+    float2 u = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+      u = f2_fma(make_float2(w[d + 3 + q], w[d + 3 + q]), make_float2(taps.up2[10 - 2 * q], taps.up2[11 - 2 * q]), u);
+    pv[d] = snake_pair(u, a, inv_b);
+  }
+  if constexpr (kEdge) {  // replicate padding of the downsampler, in registers
+    if (t0 == 0 && lane == 0) {     // s[n] = s[0] = P[2].y for n < 0 (the row's first tile)
+      const float first = pv[2].y;
+      pv[0] = pv[1] = make_float2(first, first);
+      pv[2].x = first;
+    }
+    const int i_last = n_t - t0 + 2;
+    if (i_last < 31 * kActPer) {    // s[n] = s[2T - 1] = P[i_last].x for n >= 2T (warp-uniform)
+      float mine = pv[0].x;
+#pragma unroll
+      for (int d = 1; d < kActPer; ++d) mine = (i_last & (kActPer - 1)) == d ? pv[d].x : mine;
+      const float last = __shfl_sync(0xffffffffu, mine, i_last / kActPer);
+#pragma unroll
+      for (int d = 0; d < kActPer; ++d) {
+        const int i = kActPer * lane + d;
+        if (i > i_last) pv[d] = make_float2(last, last);
+        else if (i == i_last) pv[d].y = last;
+      }
+    }
+  }
+  // ---- 3. outputs 8 lane .. 8 lane + 7 from pairs 8 lane .. 8 lane + 12
+#pragma unroll
+  for (int d = 0; d < 5; ++d)
+    pv[kActPer + d] = make_float2(__shfl_down_sync(0xffffffffu, pv[d].x, 1), __shfl_down_sync(0xffffffffu, pv[d].y, 1));
+  float out[kActPer];
+#pragma unroll
+  for (int d = 0; d < kActPer; ++d) {
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc = f2_fma(pv[d + k], make_float2(taps.down[2 * k], taps.down[2 * k + 1]), acc);
+    out[d] = acc.x + acc.y;
+  }
+  const int r0 = t0 + kActPer * lane;
+  if (lane < kActWarpOut / kActPer && (!kEdge || r0 < n_t)) {
+    float* dst = yrow + r0;
+    if (vec_st && (!kEdge || r0 + kActPer - 1 < n_t)) {
+      __stcs(reinterpret_cast<float4*>(dst), make_float4(out[0], out[1], out[2], out[3]));
+      __stcs(reinterpret_cast<float4*>(dst) + 1, make_float4(out[4], out[5], out[6], out[7]));
+    } else {
+#pragma unroll
+      for (int d = 0; d < kActPer; ++d)
+        if (r0 + d < n_t) dst[d] = out[d];
+    }
+  }
+}
+
+// grid: any number of CTAs; n_tiles = rows * tiles_per_row warp tiles, rows = batch * channels
+__global__ void __launch_bounds__(kActThreads, DMEL_ACT_MIN_CTAS) antialias_snake_kernel(const float* __restrict__ x, float* __restrict__ y, int n_t,
+                                                                      FastDiv tiles_per_row, FastDiv n_channels, unsigned n_tiles,
                                                                       const float* __restrict__ log_alpha,
-                                                                      const float* __restrict__ log_beta, ActTaps taps) {
-  __shared__ __align__(16) float xs[kActX];
-  __shared__ __align__(16) float se[kActS + 8];
-  __shared__ __align__(16) float so[kActS + 8];
+                                                                      const float* __restrict__ log_beta, const ActTaps taps) {
   grid_dependency_wait();
   grid_launch_dependents();
-  const int c = blockIdx.y, row = blockIdx.z * gridDim.y + c;
-  const int t0 = blockIdx.x * kActTile;
-  const int nt = min(kActTile, n_t - t0);
+  const int lane = threadIdx.x & 31;
+  const unsigned n_warps = gridDim.x * (kActThreads / 32);
+  unsigned tile = blockIdx.x * (kActThreads / 32) + (threadIdx.x >> 5);
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((n_t & 3) == 0);
+  const bool vec_st = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && ((n_t & 3) == 0);
+
+  unsigned row = tiles_per_row.div(min(tile, n_tiles - 1));
+  int t0 = (int)(min(tile, n_tiles - 1) - row * tiles_per_row.d) * kActWarpOut;
   const float* xr = x + (size_t)row * n_t;
-  float* yr = y + (size_t)row * n_t;
-  const float a = __expf(log_alpha[c]);
-  const float inv_b = 1.0f / (__expf(log_beta[c]) + 1e-9f);
-  const int tid = threadIdx.x;
-
-  // ---- 1. stage x[t0 - 8 + j], j in [0, kActX): 4 per thread
-  {
-    const int j0 = tid * 4, g0 = t0 - 8 + j0;
-    const bool vec = ((reinterpret_cast<uintptr_t>(xr) & 15) == 0) && ((n_t & 3) == 0) && g0 >= 0 && g0 + 3 < n_t;
-    float4 v;
-    if (vec) {
-      v = __ldg(reinterpret_cast<const float4*>(xr + g0));
-    } else {
-      v.x = __ldg(xr + min(max(g0, 0), n_t - 1));
-      v.y = __ldg(xr + min(max(g0 + 1, 0), n_t - 1));
-      v.z = __ldg(xr + min(max(g0 + 2, 0), n_t - 1));
-      v.w = __ldg(xr + min(max(g0 + 3, 0), n_t - 1));
+  float4 cur0 = act_load(xr, t0 - 8 + kActPer * lane, n_t, vec_ok), cur1 = act_load(xr, t0 - 4 + kActPer * lane, n_t, vec_ok);
+  for (; tile < n_tiles;) {
+    // the next tile's samples leave for the registers before this tile's arithmetic starts
+    const unsigned next = tile + n_warps;
+    unsigned next_row = row;
+    int next_t0 = t0;
+    float4 nxt0 = cur0, nxt1 = cur1;
+    if (next < n_tiles) {
+      next_row = tiles_per_row.div(next);
+      next_t0 = (int)(next - next_row * tiles_per_row.d) * kActWarpOut;
+#ifndef DMEL_ACT_NO_PREFETCH
+      xr = x + (size_t)next_row * n_t;
+      nxt0 = act_load(xr, next_t0 - 8 + kActPer * lane, n_t, vec_ok);
+      nxt1 = act_load(xr, next_t0 - 4 + kActPer * lane, n_t, vec_ok);
+#endif
     }
-    *reinterpret_cast<float4*>(xs + j0) = v;  // kActX == 4 * kActThreads
-  }
-  __syncthreads();
-
-  // ---- 2. activated 2x signal: entries i0 .. i0 + 3 of s_even and s_odd
-  if (tid * 4 < kActS) {
-    const int i0 = tid * 4;
-    float w[12];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(xs + i0 + 4 * q);
-      w[4 * q] = v.x, w[4 * q + 1] = v.y, w[4 * q + 2] = v.z, w[4 * q + 3] = v.w;
+    const unsigned c = row - n_channels.div(row) * n_channels.d;
+    const float a = __expf(__ldg(log_alpha + c));
+    const float inv_b = 1.0f / (__expf(__ldg(log_beta + c)) + 1e-9f);
+    float* yrow = y + (size_t)row * n_t;
+    // interior: no pair of the tile stands for a sample outside the row, and all 240 outputs exist
+    if (t0 != 0 && n_t - t0 + 2 >= 31 * kActPer) act_tile<false>(cur0, cur1, lane, t0, n_t, a, inv_b, taps, yrow, vec_st);
+    else act_tile<true>(cur0, cur1, lane, t0, n_t, a, inv_b, taps, yrow, vec_st);
+    tile = next, row = next_row, t0 = next_t0, cur0 = nxt0, cur1 = nxt1;
+#ifdef DMEL_ACT_NO_PREFETCH
+    if (tile < n_tiles) {
+      xr = x + (size_t)row * n_t;
+      cur0 = act_load(xr, t0 - 8 + kActPer * lane, n_t, vec_ok);
+      cur1 = act_load(xr, t0 - 4 + kActPer * lane, n_t, vec_ok);
     }
-    float e[4], o[4];
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      // s_even[i]: n = 2 t0 - 6 + 2 i -> m = t0 - 3 + i -> x[m - 3 + q] = xs[i + 2 + q];  s_odd[i]: x[m - 2 + q] = xs[i + 3 + q]
-      float ue = 0.f, uo = 0.f;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        ue = fmaf(w[d + 2 + q], taps.up2[11 - 2 * q], ue);
-        uo = fmaf(w[d + 3 + q], taps.up2[10 - 2 * q], uo);
-      }
-      e[d] = snake_value(ue, a, inv_b);
-      o[d] = snake_value(uo, a, inv_b);
-    }
-    *reinterpret_cast<float4*>(se + i0) = make_float4(e[0], e[1], e[2], e[3]);
-    *reinterpret_cast<float4*>(so + i0) = make_float4(o[0], o[1], o[2], o[3]);
-  }
-  __syncthreads();
-  // ---- replicate padding of the downsampler: s[n] = s[0] for n < 0 (first tile), s[n] = s[2T - 1] for n >= 2T (last tile)
-  if (t0 == 0 && tid < 3) {       // s[0] = s_even[3]
-    const float first = se[3];
-    se[tid] = first;
-    so[tid] = first;              // s_odd[i] is s[2 i - 5]: negative for i < 3
-  }
-  {  // s[2T - 1] = s_odd[i_last]; every later entry of s_even / s_odd lies past the row (the last tile, and the one
-     // before it when the last holds fewer than three outputs)
-    const int i_last = n_t - t0 + 2;
-    const int i = i_last + 1 + tid;
-    if (i_last < kActS && tid < 8 && i < kActS + 8) {
-      const float last = so[i_last];
-      se[i] = last;
-      so[i] = last;
-    }
-  }
-  __syncthreads();
-
-  // ---- 3. outputs r0 .. r0 + 3:  y[r] = sum_a G[2a + 1] s_even[r + a + 1] + G[2a] s_odd[r + a]
-  const int r0 = tid * 4;
-  if (r0 < nt) {
-    float ev[12], ov[12];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(se + r0 + 4 * q);
-      const float4 u = *reinterpret_cast<const float4*>(so + r0 + 4 * q);
-      ev[4 * q] = v.x, ev[4 * q + 1] = v.y, ev[4 * q + 2] = v.z, ev[4 * q + 3] = v.w;
-      ov[4 * q] = u.x, ov[4 * q + 1] = u.y, ov[4 * q + 2] = u.z, ov[4 * q + 3] = u.w;
-    }
-    float out[4];
-#pragma unroll
-    for (int d = 0; d < 4; ++d) {
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        acc = fmaf(ov[d + k], taps.down[2 * k], acc);
-        acc = fmaf(ev[d + k + 1], taps.down[2 * k + 1], acc);
-      }
-      out[d] = acc;
-    }
-    float* dst = yr + t0 + r0;
-    if (r0 + 3 < nt && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-      *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
-    } else {
-#pragma unroll
-      for (int d = 0; d < 4; ++d)
-        if (r0 + d < nt) dst[d] = out[d];
-    }
+#endif
   }
 }
 

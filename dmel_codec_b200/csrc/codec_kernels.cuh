@@ -68,9 +68,11 @@ __global__ void __launch_bounds__(kStreamThreads) dequantize_kernel(
 // subtraction and multiply kept un-contracted so codes are bit exact for
 // bit-identical x.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned char quantize_one(float x, float lo, float scale, float kmax) {
+// clamp(floor(pos), 0, kmax) == trunc(clamp(pos, 0, kmax + 0.5)) for every pos, NaN (-> 0) and infinities included:
+// one conversion on the XU pipe instead of a round and a conversion.  kmax_half = kmax + 0.5, exact for kmax <= 255.
+__device__ __forceinline__ unsigned char quantize_one(float x, float lo, float scale, float kmax_half) {
   const float pos = __fmul_rn(__fsub_rn(x, lo), scale);
-  return (unsigned char)fminf(fmaxf(floorf(pos), 0.f), kmax);
+  return (unsigned char)__float2int_rz(fminf(fmaxf(pos, 0.f), kmax_half));
 }
 
 __global__ void __launch_bounds__(kStreamThreads) quantize_kernel(
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(kStreamThreads) quantize_kernel(
   const unsigned n_frames = by_frames.d, n_mels = by_mels.d;
   const unsigned groups = n_elems >> 2;
   const unsigned stride = gridDim.x * kStreamThreads;
-  const float kmax = float(n_bins - 1);
+  const float kmax = float(n_bins - 1) + 0.5f;
   if (vec_ok) {
     for (unsigned g0 = blockIdx.x * kStreamThreads + threadIdx.x; g0 < groups; g0 += stride * kStreamUnroll) {
       float4 x[kStreamUnroll];
@@ -101,10 +103,15 @@ __global__ void __launch_bounds__(kStreamThreads) quantize_kernel(
         unsigned m = rowi - by_mels.div(rowi) * n_mels;
         const float xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
         unsigned char r[4];
+        float lo_m = __ldg(lo + m), scale_m = __ldg(scale + m);  // reloaded only where the group crosses into the next channel
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          r[i] = quantize_one(xs[i], __ldg(lo + m), __ldg(scale + m), kmax);
-          if (++t == n_frames) { t = 0; m = (m + 1 == n_mels) ? 0 : m + 1; }
+          r[i] = quantize_one(xs[i], lo_m, scale_m, kmax);
+          if (++t == n_frames) {
+            t = 0;
+            m = (m + 1 == n_mels) ? 0 : m + 1;
+            lo_m = __ldg(lo + m), scale_m = __ldg(scale + m);
+          }
         }
         reinterpret_cast<uchar4*>(codes)[g] = make_uchar4(r[0], r[1], r[2], r[3]);
       }

@@ -730,10 +730,14 @@ int dmel_row_peak_gain_f32(const float* wav_dev, long long n_rows, long long n_s
   if (n_rows > 65535) return fail(DMEL_ERR_INVALID, "at most 65535 rows per call, got %lld", n_rows);
   if (n_rows == 0) return DMEL_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  DeviceGuard guard(device_of(wav_dev));
+  const int dev = device_of(wav_dev);
+  DeviceGuard guard(dev);
   // the gains double as the scratch for the running maxima (bit patterns of |x|)
   DMEL_CUDA(cudaMemsetAsync(gain_dev, 0, (size_t)n_rows * sizeof(float), st));
-  const dim3 grid((unsigned)((n_samples + dmel::kAbsmaxChunk - 1) / dmel::kAbsmaxChunk), (unsigned)n_rows);
+  // about eight blocks per SM in all, each with at least kAbsmaxMinSpan samples of its row
+  const long long want = (8LL * sm_count_of(dev) + n_rows - 1) / n_rows;
+  const long long most = (n_samples + dmel::kAbsmaxMinSpan - 1) / dmel::kAbsmaxMinSpan;
+  const dim3 grid((unsigned)std::max(1LL, std::min(want, most)), (unsigned)n_rows);
   DMEL_CUDA(launch_pdl(dmel::row_absmax_kernel, grid, dim3(dmel::kAbsmaxThreads), 0, st, wav_dev, offsets_dev, lengths_dev,
                        row_stride, (int)n_samples, reinterpret_cast<unsigned*>(gain_dev)));
   DMEL_CUDA(launch_pdl(dmel::row_gain_kernel, dim3((unsigned)((n_rows + 127) / 128)), dim3(128), 0, st,
@@ -1134,10 +1138,21 @@ int dmel_fsq_encode(const float* zp_dev, long long n_rows, long long n_steps, in
     return fail(DMEL_ERR_INVALID, "bad shape (%lld, %lld, %d)", n_rows, n_steps, n_groups);
   if (n_rows == 0) return DMEL_OK;
   DeviceGuard guard(device_of(zp_dev));
-  const int tile_t = std::max(8, std::min(dmel::kFsqTileT, (40 * 1024) / (n_groups * (int)sizeof(long long))));  // indices of a tile <= 40 KB
+  const int tile_t = std::max(8, std::min(dmel::kFsqTileT, (40 * 1024) / (n_groups * (int)sizeof(int))));  // indices of a tile <= 40 KB
   const dim3 grid((unsigned)((n_steps + tile_t - 1) / tile_t), (unsigned)n_rows);
-  DMEL_CUDA(launch_pdl(dmel::fsq_encode_kernel, grid, dim3(dmel::kFsqThreads), (size_t)tile_t * n_groups * sizeof(long long),
-                       (cudaStream_t)stream, zp_dev, (int)n_steps, n_groups, lv, codes_dev, indices_dev, lm_ids_dev, codebook_size, tile_t));
+  cudaError_t e = cudaErrorInvalidValue;
+#define DMEL_FSQ_ENCODE(D)                                                                                                     \
+  case D:                                                                                                                      \
+    e = launch_pdl(dmel::fsq_encode_kernel<D>, grid, dim3(dmel::kFsqThreads), (size_t)tile_t * n_groups * sizeof(int),         \
+                   (cudaStream_t)stream, zp_dev, (int)n_steps, n_groups, lv, codes_dev, indices_dev, lm_ids_dev, codebook_size, \
+                   tile_t);                                                                                                    \
+    break;
+  switch (n_levels) {
+    DMEL_FSQ_ENCODE(1) DMEL_FSQ_ENCODE(2) DMEL_FSQ_ENCODE(3) DMEL_FSQ_ENCODE(4)
+    DMEL_FSQ_ENCODE(5) DMEL_FSQ_ENCODE(6) DMEL_FSQ_ENCODE(7) DMEL_FSQ_ENCODE(8)
+  }
+#undef DMEL_FSQ_ENCODE
+  DMEL_CUDA(e);
   return DMEL_OK;
 }
 
@@ -1152,8 +1167,18 @@ int dmel_fsq_decode(const long long* indices_dev, long long n_rows, long long n_
   if (n_rows == 0) return DMEL_OK;
   DeviceGuard guard(device_of(indices_dev));
   const dim3 grid((unsigned)((n_steps + dmel::kFsqTileT - 1) / dmel::kFsqTileT), (unsigned)n_rows);
-  DMEL_CUDA(launch_pdl(dmel::fsq_decode_kernel, grid, dim3(dmel::kFsqThreads), 0, (cudaStream_t)stream, indices_dev, (int)n_steps,
-                       n_groups, lv, codes_dev, dmel::kFsqTileT));
+  cudaError_t e = cudaErrorInvalidValue;
+#define DMEL_FSQ_DECODE(D)                                                                                                  \
+  case D:                                                                                                                   \
+    e = launch_pdl(dmel::fsq_decode_kernel<D>, grid, dim3(dmel::kFsqThreads), 0, (cudaStream_t)stream, indices_dev, (int)n_steps, \
+                   n_groups, lv, codes_dev, dmel::kFsqTileT);                                                               \
+    break;
+  switch (n_levels) {
+    DMEL_FSQ_DECODE(1) DMEL_FSQ_DECODE(2) DMEL_FSQ_DECODE(3) DMEL_FSQ_DECODE(4)
+    DMEL_FSQ_DECODE(5) DMEL_FSQ_DECODE(6) DMEL_FSQ_DECODE(7) DMEL_FSQ_DECODE(8)
+  }
+#undef DMEL_FSQ_DECODE
+  DMEL_CUDA(e);
   return DMEL_OK;
 }
 
@@ -1171,10 +1196,16 @@ int dmel_antialias_snake_f32(const float* x_dev, long long n_rows, int n_channel
     taps.up2[k] = 2.0f * up_taps_host[k];  // the x2 of UpSample1d.forward (resample.py:31), exact
     taps.down[k] = down_taps_host[k];
   }
-  DeviceGuard guard(device_of(x_dev));
-  const dim3 grid((unsigned)((n_steps + dmel::kActTile - 1) / dmel::kActTile), (unsigned)n_channels, (unsigned)n_rows);
-  DMEL_CUDA(launch_pdl(dmel::antialias_snake_kernel, grid, dim3(dmel::kActThreads), 0, (cudaStream_t)stream, x_dev, y_dev, (int)n_steps,
-                       log_alpha_dev, log_beta_dev, taps));
+  const int dev = device_of(x_dev);
+  DeviceGuard guard(dev);
+  const long long tiles_per_row = (n_steps + dmel::kActWarpOut - 1) / dmel::kActWarpOut;
+  const long long n_tiles = tiles_per_row * n_rows * n_channels;
+  if (n_tiles >= (1LL << 31)) return fail(DMEL_ERR_INVALID, "(%lld, %d, %lld) is more than 2^31 warp tiles", n_rows, n_channels, n_steps);
+  constexpr int kWarpsPerCta = dmel::kActThreads / 32;
+  const long long ctas = std::min<long long>((n_tiles + kWarpsPerCta - 1) / kWarpsPerCta, (long long)sm_count_of(dev) * 8);  // persistent: 8 CTAs per SM
+  DMEL_CUDA(launch_pdl(dmel::antialias_snake_kernel, dim3((unsigned)ctas), dim3(dmel::kActThreads), 0, (cudaStream_t)stream, x_dev, y_dev,
+                       (int)n_steps, dmel::FastDiv::make((unsigned)tiles_per_row), dmel::FastDiv::make((unsigned)n_channels),
+                       (unsigned)n_tiles, log_alpha_dev, log_beta_dev, taps));
   return DMEL_OK;
 }
 
