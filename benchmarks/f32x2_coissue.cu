@@ -21,7 +21,8 @@ __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsign
 }
 
 // KIND: 0 = 8 scalar FFMA; 1 = 4 FFMA2 (same flops); 2 = 8 FFMA + 4 ALU; 3 = 4 FFMA2 + 4 ALU;
-//       4 = 8 FFMA + 4 LDS; 5 = 4 FFMA2 + 4 LDS; 6 = 4 ALU alone; 7 = 4 LDS alone; 8 = 4 FFMA2 + 8 ALU; 9 = 8 FFMA + 8 ALU
+//       4 = 8 FFMA + 4 LDS; 5 = 4 FFMA2 + 4 LDS; 6 = 4 ALU alone; 7 = 4 LDS alone; 8 = 4 FFMA2 + 8 ALU; 9 = 8 FFMA + 8 ALU;
+//       10 = 4 FFMA2 + 4 FFMA, 11 = 4 FFMA2 + 8 FFMA (do packed and scalar FMAs share one pipe?)
 template <int KIND>
 __global__ void k(float* out, int iters, float a, float b, int ia) {
   __shared__ float sm[4096];
@@ -37,8 +38,9 @@ __global__ void k(float* out, int iters, float a, float b, int ia) {
   for (int i = 0; i < 4; ++i) y[i] = pack(x[2 * i], x[2 * i + 1]);
   const unsigned long long pa = pack(a, a), pb = pack(b, b);
   const float* sp = sm + (threadIdx.x & 31);
-  constexpr bool scalar = KIND == 0 || KIND == 2 || KIND == 4 || KIND == 9;
-  constexpr bool packed = KIND == 1 || KIND == 3 || KIND == 5 || KIND == 8;
+  constexpr bool scalar = KIND == 0 || KIND == 2 || KIND == 4 || KIND == 9 || KIND == 11;
+  constexpr bool scalar4 = KIND == 10;
+  constexpr bool packed = KIND == 1 || KIND == 3 || KIND == 5 || KIND == 8 || KIND == 10 || KIND == 11;
   constexpr int n_alu = (KIND == 2 || KIND == 3 || KIND == 6) ? 4 : ((KIND == 8 || KIND == 9) ? 8 : 0);
   constexpr bool lds = KIND == 4 || KIND == 5 || KIND == 7;
   long long t0 = clock64();
@@ -49,6 +51,10 @@ __global__ void k(float* out, int iters, float a, float b, int ia) {
       if (scalar) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], a, b);
+      }
+      if (scalar4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = fmaf(x[i], a, b);
       }
       if (packed) {
 #pragma unroll
@@ -109,5 +115,7 @@ int main() {
   run<8>("4 FFMA2 + 16 ALU");
   run<4>("8 FFMA + 4 LDS (+4 FADD)");
   run<5>("4 FFMA2 + 4 LDS (+4 FADD)");
+  run<10>("4 FFMA2 + 4 FFMA");
+  run<11>("4 FFMA2 + 8 FFMA");
   return 0;
 }

@@ -80,21 +80,50 @@ def calibrate_encode_sharded(tokenizer, n_utterances: int, load_batch: Callable[
         calibrate_sharded(tokenizer, n_utterances, load_batch, batch_size, group=group)
         yield from encode_sharded(tokenizer, n_utterances, load_batch, batch_size)
         return
-    tokenizer.quantizer.reset_stats()
-    kept = []
+    q = tokenizer.quantizer
+    q.reset_stats()
+    # Pass 1.  Batches of the shard's common padded length write straight into ONE store, so that pass 2 is a single
+    # launch over it (forty 15-microsecond launches are bound by the host, not by HBM); a batch of another length
+    # keeps its own tensor and its own launch.
+    store, used, kept = None, 0, []   # kept: (ids, lengths, row offset in the store | None, own log-mel | None)
     for ids in batches(mine, batch_size):
         item = load_batch(ids)
         audios, lengths = item if isinstance(item, (tuple, list)) else (item, None)
-        kept.append((ids, tokenizer.update_stats_keep_mel(audios, lengths), lengths))
-    tokenizer.quantizer.sync_stats(group)
-    for ids, mel, lengths in kept:
-        codes = tokenizer.quantizer.encode(mel)
+        b, t = (audios.shape[0] if audios.ndim > 1 else 1), tokenizer.n_frames(audios.shape[-1])
+        if store is None:
+            store = torch.empty((len(mine), q.n_mels, t), dtype=torch.float32, device=audios.device)
+        if store is not None and t == store.shape[2] and used + b <= store.shape[0] and audios.device == store.device:
+            tokenizer.update_stats_keep_mel(audios, lengths, out=store[used:used + b])
+            kept.append((ids, lengths, used, None))
+            used += b
+        else:
+            kept.append((ids, lengths, None, tokenizer.update_stats_keep_mel(audios, lengths)))
+    q.sync_stats(group)
+    # Pass 2: the stand-alone quantiser over the stored log-mel, then zeros past every valid length
+    codes_all = None
+    if used:
+        rows_per_call = max(1, (1 << 31) // (store.shape[1] * store.shape[2]))  # the C entry indexes with 32 bits
+        parts = [q.encode(store[r:min(r + rows_per_call, used)]) for r in range(0, used, rows_per_call)]
+        codes_all = parts[0] if len(parts) == 1 else torch.cat(parts)
+        in_store = [k for k in kept if k[2] is not None]
+        if all(k[1] is not None for k in in_store):
+            lens = torch.cat([k[1].reshape(-1).to(store.device) for k in in_store])
+            codes_all = _mask_past(codes_all, torch.div(lens, tokenizer.hop_length, rounding_mode="floor"))
+            in_store = None  # masked in one go
+    for ids, lengths, at, own in kept:
+        codes = codes_all[at:at + len(ids)] if at is not None else q.encode(own)
         code_lengths = None
         if lengths is not None:
             code_lengths = torch.div(lengths.reshape(-1).to(codes.device), tokenizer.hop_length, rounding_mode="floor")
-            t = torch.arange(codes.shape[2], device=codes.device)
-            codes = codes * (t[None, None, :] < code_lengths[:, None, None])  # the fused encode writes 0 past the valid frames
+            if at is None or in_store is not None:
+                codes = _mask_past(codes, code_lengths)
         yield ids, codes, code_lengths
+
+
+def _mask_past(codes: torch.Tensor, code_lengths: torch.Tensor) -> torch.Tensor:
+    """codes with 0 at frames >= code_lengths[b]: what the fused encode writes past the valid frames."""
+    t = torch.arange(codes.shape[2], device=codes.device)
+    return codes * (t[None, None, :] < code_lengths[:, None, None])
 
 
 # fraction of the free HBM the stored log-mel of a shard may take (the rest: waveform batches, codes, allocator slack)

@@ -156,15 +156,21 @@ class Plan:
             run_min.data_ptr(), run_max.data_ptr(), _stream_ptr(rows.device)))
 
     def logmel_minmax(self, wav: torch.Tensor, lengths: Optional[torch.Tensor], run_min: torch.Tensor,
-                      run_max: torch.Tensor) -> torch.Tensor:
-        """Log-mel of every frame, and the running per-channel min / max over the valid ones, one launch."""
+                      run_max: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Log-mel of every frame, and the running per-channel min / max over the valid ones, one launch.
+        ``out``: a contiguous float32 (B, n_mels, T) tensor to write into (e.g. a slice of a shard-sized store)."""
         _require_cuda(wav, "audio")
         rows = as_rows(wav)
         b, n = rows.shape
         t = self._frames_or_raise(n)
         _require_stat(run_min, "run_min", rows.device, self.n_mels)
         _require_stat(run_max, "run_max", rows.device, self.n_mels)
-        out = torch.empty((b, self.n_mels, t), dtype=torch.float32, device=rows.device)
+        if out is None:
+            out = torch.empty((b, self.n_mels, t), dtype=torch.float32, device=rows.device)
+        elif (tuple(out.shape) != (b, self.n_mels, t) or out.dtype != torch.float32 or out.device != rows.device
+              or not out.is_contiguous()):
+            raise ValueError(f"out must be a contiguous float32 {(b, self.n_mels, t)} tensor on {rows.device}, got "
+                             f"{out.dtype} {tuple(out.shape)} on {out.device}")
         len_ptr = self._lengths_ptr(lengths, b, rows.device)
         _native.check(_native.load().dmel_logmel_minmax_f32(
             self._handle, rows.data_ptr(), b, n, rows.stride(0) if b > 1 else n, len_ptr[0], out.data_ptr(),

@@ -200,12 +200,18 @@ class DMelTokenizer(nn.Module):
         self._plan(audios.device).update_minmax(audios, self._flat_lengths(audio_lengths), q.lo, q.hi)
 
     @torch.no_grad()
-    def update_stats_keep_mel(self, audios: Tensor, audio_lengths: Optional[Tensor] = None) -> Tensor:
+    def update_stats_keep_mel(self, audios: Tensor, audio_lengths: Optional[Tensor] = None,
+                              out: Optional[Tensor] = None) -> Tensor:
         """One calibration step that also returns the batch's log-mel (one launch), so that the encode pass of a
-        calibrate-then-encode job can quantise the stored tensor instead of running the STFT again."""
+        calibrate-then-encode job can quantise the stored tensor instead of running the STFT again.  ``out``: where
+        to write it (a contiguous (B, n_mels, T) float32 slice of a larger store)."""
         q = self.quantizer
         q._invalidate()
-        return self._plan(audios.device).logmel_minmax(audios, self._flat_lengths(audio_lengths), q.lo, q.hi)
+        return self._plan(audios.device).logmel_minmax(audios, self._flat_lengths(audio_lengths), q.lo, q.hi, out=out)
+
+    def n_frames(self, n_samples: int) -> int:
+        """Frames of an utterance of ``n_samples`` samples (reference utils/spectrogram.py:58-66: ``n // hop``)."""
+        return int(n_samples) // self.hop_length
 
     @torch.no_grad()
     def calibrate(self, batches: Iterable, group=None) -> Tuple[Tensor, Tensor]:

@@ -88,19 +88,30 @@ class _OracleTokenizer:
         self.quantizer = d.DMelQuantizer(kw["n_mels"], n_bins)
         self.quantizer.encode = lambda mel: O.dmel_encode(mel, self.quantizer.lo, self.quantizer.hi, n_bins)
 
-    def update_stats_keep_mel(self, audios, lengths=None):
+    def n_frames(self, n_samples):
+        return self.cfg.n_frames(n_samples)
+
+    def update_stats_keep_mel(self, audios, lengths=None, out=None):
         mel = self.O.log_mel(audios, self.cfg)
         n_valid = None if lengths is None else self.O.valid_frames(lengths, self.cfg.hop_length)
         lo, hi = self.O.calibrate_minmax(mel, n_valid)
         self.quantizer.set_stats(torch.minimum(self.quantizer.lo, lo), torch.maximum(self.quantizer.hi, hi))
-        return mel
+        if out is None:
+            return mel
+        assert out.shape == mel.shape and out.is_contiguous()
+        out.copy_(mel)
+        return out
 
 
 def _lengths_of(ids):
     return torch.tensor([6000 + 500 * (i % 4) for i in ids])
 
 
-def _job_worker(rank, world_size, port, n_utts, out_dir):
+def _padded(ids, ragged_tail):
+    return 9000 if ragged_tail and min(ids) >= 8 else 8000
+
+
+def _job_worker(rank, world_size, port, n_utts, out_dir, ragged_tail=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world_size)
@@ -110,7 +121,7 @@ def _job_worker(rank, world_size, port, n_utts, out_dir):
 
         def load(ids):
             lengths = _lengths_of(ids)
-            return synth.batch(ids, 8000, 16000, "speech", lengths=lengths.tolist()), lengths
+            return synth.batch(ids, _padded(ids, ragged_tail), 16000, "speech", lengths=lengths.tolist()), lengths
 
         out = [(list(ids), codes, code_lengths) for ids, codes, code_lengths in D.calibrate_encode_sharded(tok, n_utts, load, 3)]
         torch.save(out, os.path.join(out_dir, f"job{rank}.pt"))
@@ -118,18 +129,20 @@ def _job_worker(rank, world_size, port, n_utts, out_dir):
         dist.destroy_process_group()
 
 
-def test_single_transform_job_under_two_ranks(tmp_path):
+@pytest.mark.parametrize("ragged_tail", [False, True])
+def test_single_transform_job_under_two_ranks(tmp_path, ragged_tail):
     """calibrate_encode_sharded on 2 ranks == tokenising the whole set in one process with dataset-wide
-    statistics: every utterance once, in shard order, codes zero past the valid frames."""
+    statistics: every utterance once, in shard order, codes zero past the valid frames.  ragged_tail: the last batch
+    of rank 1 is padded to another length, so it cannot share the shard's log-mel store and takes the per-batch path."""
     from dmel_codec_b200 import synth
     from oracle import dmel_oracle as O
     n_utts, world_size = 10, 2
-    mp.spawn(_job_worker, args=(world_size, _free_port(), n_utts, str(tmp_path)), nprocs=world_size, join=True)
+    mp.spawn(_job_worker, args=(world_size, _free_port(), n_utts, str(tmp_path), ragged_tail), nprocs=world_size, join=True)
     kw = GOLDEN_GEOMETRY["cfg1_16k_80"]
     cfg = oracle_config(kw)
     ids = list(range(n_utts))
     lengths = _lengths_of(ids)
-    mel = O.log_mel(synth.batch(ids, 8000, 16000, "speech", lengths=lengths.tolist()), cfg)
+    mel = O.log_mel(synth.batch(ids, 9000, 16000, "speech", lengths=lengths.tolist()), cfg)
     n_valid = O.valid_frames(lengths, cfg.hop_length)
     lo, hi = O.calibrate_minmax(mel, n_valid)
     want = O.dmel_encode(mel, lo, hi, 16)
@@ -137,6 +150,8 @@ def test_single_transform_job_under_two_ranks(tmp_path):
     seen = []
     for r in range(world_size):
         for batch_ids, codes, code_lengths in torch.load(tmp_path / f"job{r}.pt"):
-            assert torch.equal(codes, want[batch_ids]) and torch.equal(code_lengths, n_valid[batch_ids])
+            t = cfg.n_frames(_padded(batch_ids, ragged_tail))
+            assert codes.shape[2] == t
+            assert torch.equal(codes, want[batch_ids][:, :, :t]) and torch.equal(code_lengths, n_valid[batch_ids])
             seen += batch_ids
     assert seen == ids
