@@ -8,7 +8,7 @@
 // One WARP = 240 consecutive outputs of one (batch, channel) row, no shared memory and no barrier.  The op is bound
 // by the FP32 pipe, not by HBM: two 12-tap FIRs and the Snake are >= 40 FMA-pipe lane-cycles per output, which at
 // 128 lanes per SM and cycle is the same rate as the HBM roofline (8 bytes per output), and every lane-cycle spent
-// on anything else comes straight out of the throughput (profiles/r2_activation_ncu_summary.txt).
+// on anything else comes straight out of the throughput (profiles/r2_standalone_kernels_ncu_summary.txt).
 //   1. lane l loads x[t0 - 8 + 8l .. + 8) with two LDG.128 (row ends through a clamped index, which IS the replicate
 //      padding of the upsampler) and fetches the eight samples that follow from lane l+1 (8 SHFL);
 //   2. it produces 8 PAIRS P[i] = (s[2 t0 - 5 + 2i], s[2 t0 - 4 + 2i]), i = 8l .. 8l+7, of the activated 2x signal s.
