@@ -951,10 +951,12 @@ static int encode_host_impl(dmel_plan* plan, const void* wav_host_v, int elem, l
     if (!plan->streams[i]) DMEL_CUDA(cudaStreamCreateWithFlags(&plan->streams[i], cudaStreamNonBlocking));
   if (!plan->d_lo) DMEL_CUDA(cudaMalloc((void**)&plan->d_lo, plan->n_mels * sizeof(float)));
   if (!plan->d_scale) DMEL_CUDA(cudaMalloc((void**)&plan->d_scale, plan->n_mels * sizeof(float)));
-  // rows per chunk: at least eight chunks per call so copies and kernels of neighbouring chunks overlap and the
-  // un-overlapped tail (last kernel + last D2H) stays short, at most 16 MiB of waveform each (DMEL_HOST_CHUNK_MB pins it)
+  // rows per chunk: about eight chunks per call so copies and kernels of neighbouring chunks overlap and the
+  // un-overlapped tail (last kernel + last D2H) stays short, but 8 to 16 MiB of waveform each (DMEL_HOST_CHUNK_MB pins
+  // it).  Measured: 61 MB of float32 in 8 MB chunks 1.24 ms, in 4 MB chunks 1.30, in 2 MB chunks 1.56; 31 MB of int16
+  // in 8 MB chunks 0.79 ms, in 4 MB chunks 0.88 - below 8 MB the copies themselves slow down.
   const long long row_bytes = n_samples * elem;
-  long long chunk_bytes = std::min<long long>(16ll << 20, std::max<long long>(2ll << 20, row_bytes * n_rows / 8));  // measured: 8 MB chunks best at 61 MB
+  long long chunk_bytes = std::min<long long>(16ll << 20, std::max<long long>(8ll << 20, row_bytes * n_rows / 8));
   if (const char* env = std::getenv("DMEL_HOST_CHUNK_MB")) chunk_bytes = (long long)std::max(1, std::atoi(env)) << 20;
   long long chunk_rows = std::max<long long>(1, chunk_bytes / row_bytes);
   chunk_rows = std::min(chunk_rows, n_rows);
