@@ -67,10 +67,14 @@ def test_cuda_activation_matches_reference_golden(native_lib, act_golden, name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(2, 5, 1008), (1, 3, 1009), (1, 2, 1010), (1, 2, 1011), (3, 4, 2016 + 7), (1, 1, 4099), (2, 2, 3)])
+@pytest.mark.parametrize("shape", [(2, 5, 1008), (1, 3, 1009), (1, 2, 1010), (1, 2, 1011), (3, 4, 2016 + 7), (1, 1, 4099), (2, 2, 3),
+                                   (1, 2, 1), (2, 3, 236), (1, 3, 239), (2, 2, 240), (1, 2, 241), (1, 2, 242), (1, 2, 243), (1, 1, 244),
+                                   (2, 3, 480), (1, 2, 481), (1, 2, 482), (3, 7, 724), (1, 1, 100000), (8, 64, 5000), (3, 50, 20001)])
 def test_cuda_activation_matches_oracle_across_tile_boundaries(native_lib, shape):
-    """row lengths around the 1008-output tile: the downsampler's replicate padding falls into the last tile, the one
-    before it, or both; odd lengths take the unaligned load / store path"""
+    """row lengths around the 240-output warp tile (and the 1008 of the first version): the downsampler's replicate
+    padding falls into the last tile, the one before it (last tile of one or two outputs), or both; lengths that are
+    not multiples of four take the unaligned load / store path; several rows and channels walk the persistent grid's
+    tile -> (row, channel) arithmetic"""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import dmel_codec_b200 as d

@@ -36,7 +36,9 @@ def test_oracle_round_trip_and_range():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,levels", [((3, 201, 10, 3), (7, 5, 5)), ((1, 64, 1, 4), (8, 5, 5, 5)), ((2, 7, 16, 2), (4, 9))])
+@pytest.mark.parametrize("shape,levels", [((3, 201, 10, 3), (7, 5, 5)), ((1, 64, 1, 4), (8, 5, 5, 5)), ((2, 7, 16, 2), (4, 9)),
+                                          ((2, 300, 3, 1), (16,)), ((1, 515, 7, 5), (3, 4, 5, 6, 7)), ((2, 33, 2, 6), (2, 3, 2, 3, 2, 3)),
+                                          ((1, 40, 5, 7), (3, 3, 3, 3, 3, 3, 3)), ((2, 1000, 12, 8), (4, 3, 3, 3, 2, 2, 2, 2))])
 def test_cuda_fsq_matches_oracle(native_lib, shape, levels):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
