@@ -10,6 +10,9 @@
 //   5  persistent grid (SMs x 8 blocks), grid-stride float4 ld.global.cs, 4 loads in flight
 //   6  16 KB chunk per 256-thread block, 4 float4 ld.global.cs per thread, no loop
 //   7  32 KB chunk per 128-thread block, 16 float4 ld.global.cs per thread in two batches of 8
+//   8  persistent grid WRITING 512 MiB (st.global.cs float4): the ceiling of a write-dominated pass such as dequantise
+//   9  persistent grid, 1 byte read per 4 bytes written (uchar4 in, float4 out): dequantise without its table lookup
+//  10  the same with 16 codes per thread (one uint4 in, four consecutive float4 out)
 // Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o build/bench/stream_read benchmarks/stream_read.cu
 #include <cstdio>
 #include <cstdlib>
@@ -104,6 +107,55 @@ __global__ void __launch_bounds__(128) chunk32k_128(const float* __restrict__ sr
   finish(m, out);
 }
 
+__global__ void __launch_bounds__(256) persistent_write(float* __restrict__ dst, size_t n4, float v) {
+  float4* q = reinterpret_cast<float4*>(dst);
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) __stcs(q + i, make_float4(v, v, v, v));
+}
+
+__global__ void __launch_bounds__(256) persistent_expand(const unsigned char* __restrict__ src, float* __restrict__ dst, size_t n4) {
+  const uchar4* in = reinterpret_cast<const uchar4*>(src);
+  float4* q = reinterpret_cast<float4*>(dst);
+  const size_t stride = (size_t)gridDim.x * 256;
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    uchar4 c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) c[u] = __ldcs(in + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) __stcs(q + i + u * stride, make_float4(c[u].x, c[u].y, c[u].z, c[u].w));
+  }
+  for (; i < n4; i += stride) {
+    const uchar4 c = __ldcs(in + i);
+    __stcs(q + i, make_float4(c.x, c.y, c.z, c.w));
+  }
+}
+
+__global__ void __launch_bounds__(256) persistent_expand16(const unsigned char* __restrict__ src, float* __restrict__ dst, size_t n16) {
+  const uint4* in = reinterpret_cast<const uint4*>(src);
+  float4* q = reinterpret_cast<float4*>(dst);
+  const size_t stride = (size_t)gridDim.x * 256;
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  for (; i + stride < n16; i += 2 * stride) {
+    uint4 c[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) c[u] = __ldcs(in + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned w[4] = {c[u].x, c[u].y, c[u].z, c[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        __stcs(q + 4 * (i + u * stride) + k, make_float4(w[k] & 255, (w[k] >> 8) & 255, (w[k] >> 16) & 255, w[k] >> 24));
+    }
+  }
+  for (; i < n16; i += stride) {
+    const uint4 c = __ldcs(in + i);
+    const unsigned w[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcs(q + 4 * i + k, make_float4(w[k] & 255, (w[k] >> 8) & 255, (w[k] >> 16) & 255, w[k] >> 24));
+  }
+}
+
 int main() {
   const size_t n = (size_t)128 << 20;  // floats: 512 MiB
   float* d;
@@ -123,6 +175,32 @@ int main() {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
+  {
+    float* w;
+    unsigned char* codes;
+    cudaMalloc(&w, n * 4);
+    cudaMalloc(&codes, n);
+    cudaMemset(codes, 3, n);
+    for (int kind = 8; kind < 11; ++kind) {
+      auto launch = [&]() {
+        if (kind == 8) persistent_write<<<sms * 8, 256>>>(w, n / 4, 1.5f);
+        else if (kind == 9) persistent_expand<<<sms * 8, 256>>>(codes, w, n / 4);
+        else persistent_expand16<<<sms * 8, 256>>>(codes, w, n / 16);
+      };
+      for (int i = 0; i < 3; ++i) launch();
+      cudaEventRecord(e0);
+      for (int i = 0; i < 10; ++i) launch();
+      cudaEventRecord(e1);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      const double bytes = kind == 8 ? n * 4.0 : n * 5.0;
+      printf("variant %d: %.1f us per launch, %.0f GB/s  (%s)\n", kind, ms * 100.f, bytes / (ms / 10 * 1e-3) / 1e9,
+             cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaFree(w);
+    cudaFree(codes);
+  }
   for (int kind = 0; kind < 8; ++kind) {
     auto launch = [&]() {
       switch (kind) {
