@@ -103,7 +103,7 @@ def calibrate_encode_sharded(tokenizer, n_utterances: int, load_batch: Callable[
     codes_all = None
     if used:
         rows_per_call = max(1, (1 << 31) // (store.shape[1] * store.shape[2]))  # the C entry indexes with 32 bits
-        parts = [q.encode(store[r:min(r + rows_per_call, used)]) for r in range(0, used, rows_per_call)]
+        parts = [q.encode(store[r:min(r + rows_per_call, used)], check_after=True) for r in range(0, used, rows_per_call)]
         codes_all = parts[0] if len(parts) == 1 else torch.cat(parts)
         in_store = [k for k in kept if k[2] is not None]
         if all(k[1] is not None for k in in_store):

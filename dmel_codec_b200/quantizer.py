@@ -114,7 +114,9 @@ class DMelQuantizer(nn.Module):
         """K / (hi - lo) per channel, 0 where the channel is degenerate."""
         if "scale" not in self._derived:
             width = self.hi - self.lo
-            k = torch.tensor(float(self.n_bins), dtype=torch.float32, device=width.device)
+            # a true float32 division K / width (scalar / tensor would be reciprocal-then-multiply: other bits); K is
+            # filled on the device, so nothing is copied from the host
+            k = torch.full_like(width, float(self.n_bins))
             self._derived["scale"] = torch.where(width > 0, k / width, torch.zeros_like(width))
         return self._derived["scale"]
 
@@ -143,10 +145,17 @@ class DMelQuantizer(nn.Module):
 
     # -- codec API (names follow reference dowmsample_fsq.py:86/:124/:135) -----
     @torch.no_grad()
-    def encode(self, z: Tensor) -> Tensor:
-        self._check_ready()
+    def encode(self, z: Tensor, *, check_after: bool = False) -> Tensor:
+        """``check_after``: queue the launch first and look at the calibration afterwards (the check reads a flag
+        back from the device; in a job that has just all-reduced the statistics that read would otherwise sit
+        between the collective and the launch with the GPU idle).  Raises all the same when uncalibrated."""
+        if not check_after:
+            self._check_ready()
         self._check_channels(z)
-        return _plan.quantize(z, self.lo, self.scale(), self.n_bins)
+        codes = _plan.quantize(z, self.lo, self.scale(), self.n_bins)
+        if check_after:
+            self._check_ready()
+        return codes
 
     @torch.no_grad()
     def decode(self, indices: Tensor) -> Tensor:

@@ -86,7 +86,7 @@ class _OracleTokenizer:
         self.O, self.cfg, self.n_bins = O, oracle_config(kw), n_bins
         self.hop_length = kw["hop_length"]
         self.quantizer = d.DMelQuantizer(kw["n_mels"], n_bins)
-        self.quantizer.encode = lambda mel: O.dmel_encode(mel, self.quantizer.lo, self.quantizer.hi, n_bins)
+        self.quantizer.encode = lambda mel, check_after=False: O.dmel_encode(mel, self.quantizer.lo, self.quantizer.hi, n_bins)
 
     def n_frames(self, n_samples):
         return self.cfg.n_frames(n_samples)
