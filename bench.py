@@ -25,6 +25,7 @@ has no quantiser.  If ``baseline/_ref`` is absent it falls back to the oracle po
 from __future__ import annotations
 
 import argparse
+import collections
 import json
 import os
 import statistics
@@ -76,12 +77,19 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def __enter__(self):
+        if os.environ.get("DMEL_BENCH_NO_CLOCKS"):  # debugging aid: no sampler process at all
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            # nvidia-smi's start-up (NVML initialisation, device enumeration) holds the driver for 0.1 - 2 s, once 24 s,
+            # and stalls whatever kernel sequence is running: wait for its first sample before the timed region begins
+            deadline = time.perf_counter() + 30.0
+            while not self.rows and self.proc.poll() is None and time.perf_counter() < deadline:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
         return self
@@ -255,22 +263,32 @@ def median_window_ms(run_window, reps: int, stream) -> list:
     """Device time of `reps` windows, each between its own pair of CUDA events (events only BETWEEN windows, so a
     window is an uninterrupted kernel sequence)."""
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    queued = [time.perf_counter()]
     marks[0].record(stream)
     for r in range(reps):
         run_window(r)
         marks[r + 1].record(stream)
+        queued.append(time.perf_counter())
     torch.cuda.synchronize()
+    if os.environ.get("DMEL_BENCH_DEBUG"):
+        print("host ms to queue each window: " + " ".join(f"{(b - a) * 1e3:.1f}" for a, b in zip(queued, queued[1:])), file=sys.stderr)
     return [marks[r].elapsed_time(marks[r + 1]) for r in range(reps)]
 
 
-def time_kernel_ms(fn, reps: int, stream) -> float:
+def time_kernel_ms(fn, reps: int, stream, keep: int = 0) -> float:
     """Median device time of one call of fn(i): every call sits between its own pair of events, the calls are queued
     back to back and the host synchronises once at the end, so the GPU never idles between them (a launch timed from
     an idle GPU carries ~15 us of ramp that no pipeline ever sees)."""
     marks = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    # keep > 0: the outputs of the last `keep` calls stay alive, so small outputs rotate through that many buffers instead
+    # of landing on the same lines of L2 (allocated by untimed calls first)
+    if keep:  # put the rotating buffers into the allocator's cache first: no cudaMalloc inside an event pair
+        warm = [fn(i) for i in range(keep + 1)]
+        del warm
+    recent = collections.deque(maxlen=max(keep, 1))
     for i, (e0, e1) in enumerate(marks):
         e0.record(stream)
-        fn(i)
+        recent.append(fn(i))
         e1.record(stream)
     torch.cuda.synchronize()
     return statistics.median(e0.elapsed_time(e1) for e0, e1 in marks)
@@ -311,11 +329,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world > 1:
         dist.barrier()
     # per-launch durations (roofline): a separate pass with an event on either side of each kernel
-    probe = max(3, min(args.steps, 200))
-    fwd_ms = time_kernel_ms(lambda i: plan.encode_decode(ring[i % RING], None, lo, scale, width, N_BINS), probe, stream)
-    enc_ms = time_kernel_ms(lambda i: plan.encode(ring[i % RING], None, lo, scale, N_BINS), probe, stream)
+    probe = max(50, min(args.steps, 200))  # 5 ms of launches: enough for a median that the ramp of the first few does not move
+    fwd_ms = time_kernel_ms(lambda i: plan.encode_decode(ring[i % RING], None, lo, scale, width, N_BINS), probe, stream, keep=8)
+    enc_ms = time_kernel_ms(lambda i: plan.encode(ring[i % RING], None, lo, scale, N_BINS), probe, stream, keep=8)
     codes0 = plan.encode(ring[0], None, lo, scale, N_BINS)
-    deq_ms = time_kernel_ms(lambda i: P.dequantize(codes0, table), probe, stream)
+    deq_ms = time_kernel_ms(lambda i: P.dequantize(codes0, table), probe, stream, keep=8)
     if world > 1:
         dist.barrier()
 
@@ -324,8 +342,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     with ClockSampler(local_rank) as clocks:
         torch.cuda.synchronize()
         wall0 = time.perf_counter()
-        windows = median_window_ms(lambda r: [step(args.warmup + r * args.steps + i) for i in range(args.steps)], reps, stream)
+        # the outputs of the last 8 steps stay alive, so the allocator hands every step a buffer that was last written
+        # eight steps (8 x 38 MB > L2) ago; keeping ALL of a window's outputs alive, as a list comprehension does, makes
+        # the first window allocate K x 38 MB of fresh HBM (7 - 24 s of cudaMalloc at K = 2000)
+        recent = collections.deque(maxlen=8)
+
+        def window(r):
+            for i in range(args.steps):
+                recent.append(step(args.warmup + r * args.steps + i))
+
+        windows = median_window_ms(window, reps, stream)
+        recent.clear()
         wall = time.perf_counter() - wall0
+    if os.environ.get("DMEL_BENCH_DEBUG"):
+        print(f"[rank {rank}] windows (ms): " + " ".join(f"{w:.3f}" for w in windows), file=sys.stderr)
     if world > 1:
         dist.barrier()
     t = torch.tensor([statistics.median(windows), min(windows), max(windows), wall * 1e3 / reps, fwd_ms, enc_ms, deq_ms],
@@ -399,7 +429,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 for i in range(3):
                     ref_step(i)
                 k = max(3, min(args.steps, 50))
-                ms = statistics.median(median_window_ms(lambda r: [ref_step(r * k + i) for i in range(k)], 5, stream)) / k
+                def ref_window(r):
+                    for i in range(k):
+                        ref_step(r * k + i)
+
+                ms = statistics.median(median_window_ms(ref_window, 5, stream)) / k
             g = torch.tensor([ms], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(g, op=dist.ReduceOp.MAX)
