@@ -281,7 +281,10 @@ int dmel_tensor_minmax_f32(const float* logmel_dev, long long n_rows, int n_mels
  *   zp_dev      (B, T, G, D) float32, D = n_levels <= 8
  *   codes_dev   (B, T, G, D) float32 in [-1, 1], or NULL
  *   indices_dev (B, G, T) int64 in [0, prod(levels)): the layout DownsampleFiniteScalarQuantize.encode returns; or NULL
- *   lm_ids_dev  (B, T, G) int64 = index + g * codebook_size, or NULL */
+ *   lm_ids_dev  (B, T, G) int64 = index + g * codebook_size, or NULL
+ * tanh is evaluated as 1 - 2 / (1 + e^{2x}) on the hardware's ex2 / rcp approximations (absolute error below 2e-7, the size
+ * of tanhf's own last bit): a level can differ from a float32 tanhf implementation only where tanh(z + shift) * half_l - offset
+ * lies within ~1e-6 of a rounding boundary (x.5), the same caveat any two float32 tanh implementations carry. */
 int dmel_fsq_encode(const float* zp_dev, long long n_rows, long long n_steps, int n_groups, const int* levels,
                     int n_levels, float* codes_dev, long long* indices_dev, long long* lm_ids_dev, int codebook_size,
                     void* stream);
