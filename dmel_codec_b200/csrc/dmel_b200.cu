@@ -92,6 +92,9 @@ struct dmel_plan {
   int32_t* d_len[2] = {nullptr, nullptr};
   float* d_lo = nullptr;
   float* d_scale = nullptr;
+  std::vector<float> host_stats;  // the lo / scale values d_lo / d_scale hold (2 * n_mels), empty = nothing uploaded yet
+  cudaEvent_t chunk_in[2] = {nullptr, nullptr};    // host pipeline: the slot's waveform has arrived
+  cudaEvent_t chunk_used[2] = {nullptr, nullptr};  //                the slot's kernel has consumed it
   size_t wav_cap = 0, codes_cap = 0, len_cap = 0;
 };
 
@@ -472,6 +475,10 @@ void dmel_plan_destroy(dmel_plan* plan) {
     if (plan->streams[i]) cudaStreamDestroy(plan->streams[i]);
   }
   if (plan->stats_ready) cudaEventDestroy(plan->stats_ready);
+  for (int i = 0; i < 2; ++i) {
+    if (plan->chunk_in[i]) cudaEventDestroy(plan->chunk_in[i]);
+    if (plan->chunk_used[i]) cudaEventDestroy(plan->chunk_used[i]);
+  }
   cudaFree(plan->d_lo);
   cudaFree(plan->d_scale);
   delete plan;
@@ -986,42 +993,70 @@ static int encode_host_impl(dmel_plan* plan, const void* wav_host_v, int elem, l
     }
     plan->len_cap = chunk_rows;
   }
-  // both streams were synchronised when the previous call returned, so nothing still reads d_lo / d_scale; the
-  // second stream waits for the statistics through an event instead of a host synchronisation
-  DMEL_CUDA(cudaMemcpyAsync(plan->d_lo, lo_host, plan->n_mels * sizeof(float), cudaMemcpyHostToDevice, plan->streams[0]));
-  DMEL_CUDA(cudaMemcpyAsync(plan->d_scale, scale_host, plan->n_mels * sizeof(float), cudaMemcpyHostToDevice, plan->streams[0]));
-  if (!plan->stats_ready) DMEL_CUDA(cudaEventCreateWithFlags(&plan->stats_ready, cudaEventDisableTiming));
-  DMEL_CUDA(cudaEventRecord(plan->stats_ready, plan->streams[0]));
-  DMEL_CUDA(cudaStreamWaitEvent(plan->streams[1], plan->stats_ready, 0));
+  // The statistics go up only when they differ from what the device already holds: a tokeniser encodes thousands of
+  // batches per calibration, and two copies from pageable host memory are 20-30 us of every call.  Both streams
+  // were synchronised when the previous call returned, so nothing still reads d_lo / d_scale; the second stream waits
+  // for the upload through an event instead of a host synchronisation.
+  const size_t nm = (size_t)plan->n_mels;
+  const bool same_stats = plan->host_stats.size() == 2 * nm &&
+                          std::memcmp(plan->host_stats.data(), lo_host, nm * sizeof(float)) == 0 &&
+                          std::memcmp(plan->host_stats.data() + nm, scale_host, nm * sizeof(float)) == 0;
+  if (!same_stats) {
+    plan->host_stats.clear();  // stays empty if an upload fails
+    DMEL_CUDA(cudaMemcpyAsync(plan->d_lo, lo_host, nm * sizeof(float), cudaMemcpyHostToDevice, plan->streams[0]));
+    DMEL_CUDA(cudaMemcpyAsync(plan->d_scale, scale_host, nm * sizeof(float), cudaMemcpyHostToDevice, plan->streams[0]));
+    if (!plan->stats_ready) DMEL_CUDA(cudaEventCreateWithFlags(&plan->stats_ready, cudaEventDisableTiming));
+    DMEL_CUDA(cudaEventRecord(plan->stats_ready, plan->streams[0]));
+    DMEL_CUDA(cudaStreamWaitEvent(plan->streams[1], plan->stats_ready, 0));
+    plan->host_stats.assign(lo_host, lo_host + nm);
+    plan->host_stats.insert(plan->host_stats.end(), scale_host, scale_host + nm);
+  }
   // From here on copies into the caller's host buffers may be in flight on both streams: every exit, error or
   // not, goes through the two synchronisations below.
-  auto queue_chunk = [&](long long r0, int slot) -> int {
-    const long long rows = std::min(chunk_rows, n_rows - r0);
-    cudaStream_t st = plan->streams[slot];
-    // stream order already guarantees the slot's previous D2H finished before this H2D starts
+  // Stream 0 carries every host-to-device copy, back to back; stream 1 the kernels and the copies back.  (With each
+  // chunk's copy, kernel and copy-back in one stream and the chunks alternating between two streams, as in the first
+  // version, consecutive copies sit on different streams and the copy engine idles ~14 us between them.)
+  // DMEL_HOST_PIPELINE=alternate selects that first form.
+  static const bool alternate = std::getenv("DMEL_HOST_PIPELINE") && std::strcmp(std::getenv("DMEL_HOST_PIPELINE"), "alternate") == 0;
+  for (int i = 0; i < 2; ++i) {
+    if (!plan->chunk_in[i]) DMEL_CUDA(cudaEventCreateWithFlags(&plan->chunk_in[i], cudaEventDisableTiming));
+    if (!plan->chunk_used[i]) DMEL_CUDA(cudaEventCreateWithFlags(&plan->chunk_used[i], cudaEventDisableTiming));
+  }
+  auto queue_chunk = [&](long long r0, long long rows, int slot, long long index) -> int {
+    cudaStream_t s_in = alternate ? plan->streams[slot] : plan->streams[0];
+    cudaStream_t s_run = alternate ? plan->streams[slot] : plan->streams[1];
+    // the slot's buffers are free once the kernel of chunk index - 2 has run (alternate: stream order says so)
+    if (!alternate && index >= 2) DMEL_CUDA(cudaStreamWaitEvent(s_in, plan->chunk_used[slot], 0));
     if (row_stride == n_samples)
       DMEL_CUDA(cudaMemcpyAsync(plan->d_wav[slot], wav_host + r0 * row_stride * elem, (size_t)rows * n_samples * elem,
-                                cudaMemcpyHostToDevice, st));
+                                cudaMemcpyHostToDevice, s_in));
     else
       DMEL_CUDA(cudaMemcpy2DAsync(plan->d_wav[slot], n_samples * elem, wav_host + r0 * row_stride * elem, row_stride * elem,
-                                  n_samples * elem, rows, cudaMemcpyHostToDevice, st));
+                                  n_samples * elem, rows, cudaMemcpyHostToDevice, s_in));
     const int32_t* len_dev = nullptr;
     if (lengths_host) {
-      DMEL_CUDA(cudaMemcpyAsync(plan->d_len[slot], lengths_host + r0, rows * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+      DMEL_CUDA(cudaMemcpyAsync(plan->d_len[slot], lengths_host + r0, rows * sizeof(int32_t), cudaMemcpyHostToDevice, s_in));
       len_dev = plan->d_len[slot];
     }
+    if (!alternate) {
+      DMEL_CUDA(cudaEventRecord(plan->chunk_in[slot], s_in));
+      DMEL_CUDA(cudaStreamWaitEvent(s_run, plan->chunk_in[slot], 0));
+    }
     const int rc_k = elem == 2 ? dmel_encode_pcm16_u8(plan, reinterpret_cast<const int16_t*>(plan->d_wav[slot]), rows, n_samples,
-                                                      n_samples, len_dev, plan->d_lo, plan->d_scale, n_bins, plan->d_codes[slot], st)
+                                                      n_samples, len_dev, plan->d_lo, plan->d_scale, n_bins, plan->d_codes[slot], s_run)
                                : dmel_encode_u8(plan, plan->d_wav[slot], rows, n_samples, n_samples, len_dev, plan->d_lo,
-                                                plan->d_scale, n_bins, plan->d_codes[slot], nullptr, nullptr, 0.f, st);
+                                                plan->d_scale, n_bins, plan->d_codes[slot], nullptr, nullptr, 0.f, s_run);
     if (rc_k != DMEL_OK) return rc_k;
+    if (!alternate) DMEL_CUDA(cudaEventRecord(plan->chunk_used[slot], s_run));
     DMEL_CUDA(cudaMemcpyAsync(codes_host + (size_t)r0 * plan->n_mels * T, plan->d_codes[slot],
-                              (size_t)rows * plan->n_mels * T, cudaMemcpyDeviceToHost, st));
+                              (size_t)rows * plan->n_mels * T, cudaMemcpyDeviceToHost, s_run));
     return DMEL_OK;
   };
   int slot = 0;
+  long long index = 0;
   rc = DMEL_OK;
-  for (long long r0 = 0; r0 < n_rows && rc == DMEL_OK; r0 += chunk_rows, slot ^= 1) rc = queue_chunk(r0, slot);
+  for (long long r0 = 0; r0 < n_rows && rc == DMEL_OK; r0 += chunk_rows, slot ^= 1, ++index)
+    rc = queue_chunk(r0, std::min(chunk_rows, n_rows - r0), slot, index);
   const std::string queued_error = rc == DMEL_OK ? std::string() : g_last_error;
   const cudaError_t s0 = cudaStreamSynchronize(plan->streams[0]);
   const cudaError_t s1 = cudaStreamSynchronize(plan->streams[1]);

@@ -235,6 +235,25 @@ def test_encode_host_matches_device_path(d):
     assert torch.equal(tok.encode_host(wav, lengths), want.cpu())
 
 
+def test_encode_host_follows_a_change_of_statistics(d):
+    """the library keeps the statistics it last uploaded and skips the upload when a call brings the same values:
+    new values (another calibration, another tokenizer on the same plan geometry) must reach the device"""
+    from dmel_codec_b200 import synth
+    kw = GOLDEN_GEOMETRY["cfg1_16k_80"]
+    wav = synth.batch(range(600, 606), 32000, 16000, "speech")
+    tok = _tokenizer(d, kw, 16)
+    tok.calibrate([wav.cuda()])
+    first = tok.encode_host(wav)
+    assert torch.equal(first, tok.encode(wav.cuda())[0].cpu())
+    assert torch.equal(tok.encode_host(wav), first)                      # same statistics: the cached upload
+    q = tok.quantizer
+    q.set_stats(q.lo - 1.5, q.hi + 0.75)
+    second = tok.encode_host(wav)
+    assert torch.equal(second, tok.encode(wav.cuda())[0].cpu()) and not torch.equal(second, first)
+    q.set_stats(q.lo + 1.5, q.hi - 0.75)                                  # and back
+    assert torch.equal(tok.encode_host(wav), first)
+
+
 def test_quantizer_edge_cases(d):
     q = d.DMelQuantizer(3, 16).cuda()
     q.set_stats(torch.tensor([-11.5, 0.0, 2.0]), torch.tensor([1.0, 0.0, 3.0]))  # channel 1 is degenerate
