@@ -14,7 +14,7 @@ from ctypes import (POINTER, c_char_p, c_float, c_int, c_int32, c_longlong, c_ui
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DMEL_LIB") or os.path.join(_HERE, "libdmel_b200.so")  # DMEL_LIB: A/B builds
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = -1, -2, -3, -4
 
 class DmelIO(ctypes.Structure):
@@ -80,6 +80,8 @@ SIGNATURES = {
                                          c_void_p, c_void_p]),
     "dmel_quantize_u8": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p]),
+    "dmel_quantize_masked_u8": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_int,
+                                        c_void_p, c_void_p]),
     "dmel_dequantize_f32": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_int, c_void_p,
                                     c_void_p]),
     "dmel_tensor_minmax_f32": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p,

@@ -75,10 +75,14 @@ __device__ __forceinline__ unsigned char quantize_one(float x, float lo, float s
   return (unsigned char)__float2int_rz(fminf(fmaxf(pos, 0.f), kmax_half));
 }
 
+// n_valid (frames per batch row, or nullptr): frames at or past it get code 0 and their log-mel is never read - the
+// padded part of a right-padded batch costs one byte of traffic per value instead of five.  kMasked = false compiles
+// the length bookkeeping out (it costs the plain kernel 16 points of its HBM fraction otherwise).
+template <bool kMasked>
 __global__ void __launch_bounds__(kStreamThreads) quantize_kernel(
     const float* __restrict__ mel, uint8_t* __restrict__ codes, const float* __restrict__ lo,
     const float* __restrict__ scale, unsigned n_elems, FastDiv by_frames, FastDiv by_mels,
-    unsigned n_bins, bool vec_ok) {
+    unsigned n_bins, bool vec_ok, const int* __restrict__ n_valid) {
   grid_dependency_wait();   // programmatic dependent launch: the inputs may come from the previous kernel
   grid_launch_dependents();
   const unsigned n_frames = by_frames.d, n_mels = by_mels.d;
@@ -88,29 +92,45 @@ __global__ void __launch_bounds__(kStreamThreads) quantize_kernel(
   if (vec_ok) {
     for (unsigned g0 = blockIdx.x * kStreamThreads + threadIdx.x; g0 < groups; g0 += stride * kStreamUnroll) {
       float4 x[kStreamUnroll];
+      unsigned rowi[kStreamUnroll], t0[kStreamUnroll], nv[kStreamUnroll];
 #pragma unroll
       for (int u = 0; u < kStreamUnroll; ++u) {
         const unsigned g = g0 + u * stride;
-        x[u] = g < groups ? __ldcs(reinterpret_cast<const float4*>(mel) + g) : make_float4(0, 0, 0, 0);
+        const unsigned e = g << 2;
+        rowi[u] = by_frames.div(e);
+        t0[u] = e - rowi[u] * n_frames;
+        nv[u] = n_frames;
+        if (kMasked && g < groups) {
+          const int v = __ldg(n_valid + by_mels.div(rowi[u]));
+          nv[u] = v < 0 ? 0u : min((unsigned)v, n_frames);
+        }
+        // a group wholly past its row's valid frames (and not running into the next row) is not read at all
+        const bool dead = kMasked && t0[u] >= nv[u] && t0[u] + 4 <= n_frames;
+        x[u] = (g < groups && !dead) ? __ldcs(reinterpret_cast<const float4*>(mel) + g) : make_float4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int u = 0; u < kStreamUnroll; ++u) {
         const unsigned g = g0 + u * stride;
         if (g >= groups) continue;
-        const unsigned e = g << 2;
-        const unsigned rowi = by_frames.div(e);
-        unsigned t = e - rowi * n_frames;
-        unsigned m = rowi - by_mels.div(rowi) * n_mels;
+        unsigned t = t0[u];
+        unsigned row = rowi[u];
+        unsigned m = row - by_mels.div(row) * n_mels;
+        unsigned valid = nv[u];
         const float xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
         unsigned char r[4];
         float lo_m = __ldg(lo + m), scale_m = __ldg(scale + m);  // reloaded only where the group crosses into the next channel
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          r[i] = quantize_one(xs[i], lo_m, scale_m, kmax);
+          r[i] = (!kMasked || t < valid) ? quantize_one(xs[i], lo_m, scale_m, kmax) : (unsigned char)0;
           if (++t == n_frames) {
             t = 0;
+            ++row;
             m = (m + 1 == n_mels) ? 0 : m + 1;
             lo_m = __ldg(lo + m), scale_m = __ldg(scale + m);
+            if (kMasked && m == 0) {  // crossed into the next batch row (it exists: the group lies inside the tensor)
+              const int v = __ldg(n_valid + by_mels.div(row));
+              valid = v < 0 ? 0u : min((unsigned)v, n_frames);
+            }
           }
         }
         reinterpret_cast<uchar4*>(codes)[g] = make_uchar4(r[0], r[1], r[2], r[3]);
@@ -120,8 +140,11 @@ __global__ void __launch_bounds__(kStreamThreads) quantize_kernel(
   const unsigned first = vec_ok ? (groups << 2) : 0;
   for (unsigned e = first + blockIdx.x * kStreamThreads + threadIdx.x; e < n_elems; e += stride) {
     const unsigned rowi = by_frames.div(e);
-    const unsigned m = rowi - by_mels.div(rowi) * n_mels;
-    codes[e] = quantize_one(mel[e], __ldg(lo + m), __ldg(scale + m), kmax);
+    const unsigned b = by_mels.div(rowi);
+    const unsigned m = rowi - b * n_mels;
+    const unsigned t = e - rowi * n_frames;
+    const bool live = !kMasked || (int)t < __ldg(n_valid + b);
+    codes[e] = live ? quantize_one(mel[e], __ldg(lo + m), __ldg(scale + m), kmax) : (unsigned char)0;
   }
 }
 

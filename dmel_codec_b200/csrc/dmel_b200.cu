@@ -1095,6 +1095,12 @@ static int check_tensor(const void* a, const void* b, long long n_rows, int n_me
 int dmel_quantize_u8(const float* logmel_dev, long long n_rows, int n_mels, long long n_frames,
                      const float* lo_dev, const float* scale_dev, int n_bins, uint8_t* codes_dev,
                      void* stream) {
+  return dmel_quantize_masked_u8(logmel_dev, n_rows, n_mels, n_frames, nullptr, lo_dev, scale_dev, n_bins, codes_dev, stream);
+}
+
+int dmel_quantize_masked_u8(const float* logmel_dev, long long n_rows, int n_mels, long long n_frames,
+                            const int32_t* n_valid_dev, const float* lo_dev, const float* scale_dev, int n_bins,
+                            uint8_t* codes_dev, void* stream) {
   unsigned n = 0;
   int rc = check_tensor(logmel_dev, codes_dev, n_rows, n_mels, n_frames, &n);
   if (rc != DMEL_OK) return rc;
@@ -1104,9 +1110,10 @@ int dmel_quantize_u8(const float* logmel_dev, long long n_rows, int n_mels, long
   const bool vec = ((reinterpret_cast<uintptr_t>(logmel_dev) & 15) == 0) && ((reinterpret_cast<uintptr_t>(codes_dev) & 3) == 0);
   const int dev = device_of(logmel_dev);
   DeviceGuard guard(dev);
-  DMEL_CUDA(launch_pdl(dmel::quantize_kernel, dim3(stream_grid(dev, n >> 2)), dim3(dmel::kStreamThreads), 0, (cudaStream_t)stream,
+  auto* kernel = n_valid_dev ? dmel::quantize_kernel<true> : dmel::quantize_kernel<false>;
+  DMEL_CUDA(launch_pdl(kernel, dim3(stream_grid(dev, n >> 2)), dim3(dmel::kStreamThreads), 0, (cudaStream_t)stream,
                        logmel_dev, codes_dev, lo_dev, scale_dev, n, dmel::FastDiv::make((unsigned)n_frames),
-                       dmel::FastDiv::make((unsigned)n_mels), (unsigned)n_bins, vec));
+                       dmel::FastDiv::make((unsigned)n_mels), (unsigned)n_bins, vec, n_valid_dev));
   return DMEL_OK;
 }
 

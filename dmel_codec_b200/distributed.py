@@ -99,24 +99,29 @@ def calibrate_encode_sharded(tokenizer, n_utterances: int, load_batch: Callable[
         else:
             kept.append((ids, lengths, None, tokenizer.update_stats_keep_mel(audios, lengths)))
     q.sync_stats(group)
-    # Pass 2: the stand-alone quantiser over the stored log-mel, then zeros past every valid length
+    # Pass 2: the stand-alone quantiser over the stored log-mel; frames past a valid length get code 0 unread
     codes_all = None
     if used:
-        rows_per_call = max(1, (1 << 31) // (store.shape[1] * store.shape[2]))  # the C entry indexes with 32 bits
-        parts = [q.encode(store[r:min(r + rows_per_call, used)], check_after=True) for r in range(0, used, rows_per_call)]
-        codes_all = parts[0] if len(parts) == 1 else torch.cat(parts)
         in_store = [k for k in kept if k[2] is not None]
+        lens = None
         if all(k[1] is not None for k in in_store):
-            lens = torch.cat([k[1].reshape(-1).to(store.device) for k in in_store])
-            codes_all = _mask_past(codes_all, torch.div(lens, tokenizer.hop_length, rounding_mode="floor"))
-            in_store = None  # masked in one go
+            lens = torch.div(torch.cat([k[1].reshape(-1).to(store.device) for k in in_store]), tokenizer.hop_length,
+                             rounding_mode="floor")
+        rows_per_call = max(1, ((1 << 31) - 1) // (store.shape[1] * store.shape[2]))  # the C entry indexes with 32 bits
+        parts = [q.encode(store[r:min(r + rows_per_call, used)], None if lens is None else lens[r:min(r + rows_per_call, used)],
+                          check_after=True) for r in range(0, used, rows_per_call)]
+        codes_all = parts[0] if len(parts) == 1 else torch.cat(parts)
     for ids, lengths, at, own in kept:
-        codes = codes_all[at:at + len(ids)] if at is not None else q.encode(own)
         code_lengths = None
         if lengths is not None:
-            code_lengths = torch.div(lengths.reshape(-1).to(codes.device), tokenizer.hop_length, rounding_mode="floor")
-            if at is None or in_store is not None:
+            code_lengths = torch.div(lengths.reshape(-1).to(store.device if at is not None else own.device), tokenizer.hop_length,
+                                     rounding_mode="floor")
+        if at is not None:
+            codes = codes_all[at:at + len(ids)]
+            if lens is None and code_lengths is not None:   # a store that mixes batches with and without lengths
                 codes = _mask_past(codes, code_lengths)
+        else:
+            codes = q.encode(own, code_lengths)
         yield ids, codes, code_lengths
 
 

@@ -386,7 +386,9 @@ class Plan:
 # ---------------------------------------------------------------------------
 # tensor-level quantiser stages (no plan needed)
 # ---------------------------------------------------------------------------
-def quantize(mel: torch.Tensor, lo: torch.Tensor, scale: torch.Tensor, n_bins: int) -> torch.Tensor:
+def quantize(mel: torch.Tensor, lo: torch.Tensor, scale: torch.Tensor, n_bins: int,
+             n_valid: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``n_valid``: valid frames per batch row (B integers); frames at or past it get code 0 and are not read."""
     _require_cuda(mel, "mel")
     if mel.ndim != 3:
         raise ValueError(f"expected (B, n_mels, T), got {tuple(mel.shape)}")
@@ -394,11 +396,17 @@ def quantize(mel: torch.Tensor, lo: torch.Tensor, scale: torch.Tensor, n_bins: i
     b, m, t = x.shape
     _require_stat(lo, "lo", x.device, m)
     _require_stat(scale, "scale", x.device, m)
+    nv = None
+    if n_valid is not None:
+        nv = n_valid.detach().reshape(-1).to(device=x.device, dtype=torch.int32).contiguous()
+        if nv.numel() != b:
+            raise ValueError(f"n_valid has {nv.numel()} entries for a batch of {b}")
+        nv.record_stream(torch.cuda.current_stream(x.device))
     codes = torch.empty((b, m, t), dtype=torch.uint8, device=x.device)
     if x.numel():
-        _native.check(_native.load().dmel_quantize_u8(
-            x.data_ptr(), b, m, t, lo.data_ptr(), scale.data_ptr(), int(n_bins), codes.data_ptr(),
-            _stream_ptr(x.device)))
+        _native.check(_native.load().dmel_quantize_masked_u8(
+            x.data_ptr(), b, m, t, nv.data_ptr() if nv is not None else None, lo.data_ptr(), scale.data_ptr(), int(n_bins),
+            codes.data_ptr(), _stream_ptr(x.device)))
     return codes
 
 

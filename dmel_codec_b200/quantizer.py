@@ -145,14 +145,15 @@ class DMelQuantizer(nn.Module):
 
     # -- codec API (names follow reference dowmsample_fsq.py:86/:124/:135) -----
     @torch.no_grad()
-    def encode(self, z: Tensor, *, check_after: bool = False) -> Tensor:
-        """``check_after``: queue the launch first and look at the calibration afterwards (the check reads a flag
+    def encode(self, z: Tensor, mel_lengths: Optional[Tensor] = None, *, check_after: bool = False) -> Tensor:
+        """``mel_lengths``: valid frames per batch row; frames at or past it get code 0 (what the fused encode
+        writes there) without their log-mel being read.  ``check_after``: queue the launch first and look at the calibration afterwards (the check reads a flag
         back from the device; in a job that has just all-reduced the statistics that read would otherwise sit
         between the collective and the launch with the GPU idle).  Raises all the same when uncalibrated."""
         if not check_after:
             self._check_ready()
         self._check_channels(z)
-        codes = _plan.quantize(z, self.lo, self.scale(), self.n_bins)
+        codes = _plan.quantize(z, self.lo, self.scale(), self.n_bins, n_valid=mel_lengths)
         if check_after:
             self._check_ready()
         return codes

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DMEL_ABI_VERSION 8
+#define DMEL_ABI_VERSION 9
 
 #define DMEL_OK 0
 #define DMEL_ERR_INVALID (-1)     /* bad argument (shape, null pointer, L <= reflect pad ...) */
@@ -261,6 +261,13 @@ int dmel_row_peak_gain_f32(const float* wav_dev, long long n_rows, long long n_s
 int dmel_quantize_u8(const float* logmel_dev, long long n_rows, int n_mels, long long n_frames,
                      const float* lo_dev, const float* scale_dev, int n_bins,
                      uint8_t* codes_dev, void* stream);
+/* The same with a valid-frame count per batch row (n_valid_dev: n_rows int32, or NULL = dmel_quantize_u8): frames at
+ * or past it get code 0, which is what the fused encode writes there, and their log-mel is not read.  Pass 2 of the
+ * calibrate-then-encode job over right-padded batches (reference collate: dataset/lhotse_tts_dataset.py:46-65; the
+ * valid-frame rule: models/codec_lit_modules.py:176-177). */
+int dmel_quantize_masked_u8(const float* logmel_dev, long long n_rows, int n_mels, long long n_frames,
+                            const int32_t* n_valid_dev, const float* lo_dev, const float* scale_dev, int n_bins,
+                            uint8_t* codes_dev, void* stream);
 
 /* codes -> bin-centre log-mel.  table_dev is (n_mels, n_bins) float32:
  * table[c][k] = lo_c + (k + 0.5) * (hi_c - lo_c) / K.  Codes >= n_bins read as n_bins-1. */

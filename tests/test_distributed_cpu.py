@@ -86,7 +86,13 @@ class _OracleTokenizer:
         self.O, self.cfg, self.n_bins = O, oracle_config(kw), n_bins
         self.hop_length = kw["hop_length"]
         self.quantizer = d.DMelQuantizer(kw["n_mels"], n_bins)
-        self.quantizer.encode = lambda mel, check_after=False: O.dmel_encode(mel, self.quantizer.lo, self.quantizer.hi, n_bins)
+        def encode(mel, mel_lengths=None, check_after=False):
+            codes = O.dmel_encode(mel, self.quantizer.lo, self.quantizer.hi, n_bins)
+            if mel_lengths is not None:
+                codes = codes * (torch.arange(codes.shape[2])[None, None, :] < mel_lengths.reshape(-1)[:, None, None])
+            return codes
+
+        self.quantizer.encode = encode
 
     def n_frames(self, n_samples):
         return self.cfg.n_frames(n_samples)

@@ -31,6 +31,33 @@ def quant_golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "quantizer_golden.npz"))
 
 
+@pytest.mark.parametrize("shape", [(5, 7, 33), (3, 80, 626), (4, 16, 1), (2, 3, 10), (6, 128, 937)])
+@pytest.mark.parametrize("aligned", [True, False])
+def test_length_aware_quantiser_equals_quantise_then_mask(d, shape, aligned):
+    """dmel_quantize_masked_u8: code 0 at and past each row's valid-frame count (0, negative and oversized counts
+    included), the plain quantiser's codes before it; groups of four that cross a channel or batch row, and tensors
+    off a 16-byte boundary (the scalar path)"""
+    from dmel_codec_b200 import plan as P
+    b, m, t = shape
+    g = torch.Generator().manual_seed(b * 1000 + m * 10 + t)
+    n = b * m * t
+    flat = torch.empty(n + 3, device="cuda")
+    flat.copy_(torch.randn(n + 3, generator=g) * 4 - 5)
+    mel = (flat[:n] if aligned else flat[3:3 + n]).view(b, m, t)
+    lo = (torch.randn(m, generator=g) - 9).cuda()
+    hi = lo + torch.rand(m, generator=g).cuda() * 10 + 0.5
+    scale = torch.full_like(lo, 16.0) / (hi - lo)
+    nv = torch.randint(-1, t + 3, (b,), generator=g, dtype=torch.int32)
+    nv[0] = 0
+    if b > 1:
+        nv[1] = t
+    plain = P.quantize(mel, lo, scale, 16)
+    want = plain * (torch.arange(t, device="cuda")[None, None, :] < nv.cuda().clamp(0, t)[:, None, None])
+    got = P.quantize(mel, lo, scale, 16, n_valid=nv)
+    assert torch.equal(got, want)
+    assert torch.equal(P.quantize(mel, lo, scale, 16, n_valid=torch.full((b,), t)), plain)
+
+
 # ---------------------------------------------------------------------------
 # (d) the frozen quantiser spec: stand-alone kernels bit for bit, fused encode up to edge ambiguity
 # ---------------------------------------------------------------------------
