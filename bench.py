@@ -642,7 +642,7 @@ def pool_workload(name, rank, world, dev):
 
     job()
     times = []
-    for _ in range(5):
+    for _ in range(9):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -671,7 +671,7 @@ def pool_workload(name, rank, world, dev):
            "config": {"workload": label, "launch": tok._plan(dev).describe(),
                       "job": "two transform passes" if two_pass else
                              "one transform pass (log-mel of the shard kept in HBM) + stand-alone quantiser pass",
-                      "data": f"pool of {pool_n} distinct synthetic utterances per rank, cycled; median of 5 runs"}}
+                      "data": f"pool of {pool_n} distinct synthetic utterances per rank, cycled; median of 9 runs"}}
     del pool, tok
     torch.cuda.empty_cache()
     return out
