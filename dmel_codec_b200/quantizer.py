@@ -108,7 +108,7 @@ class DMelQuantizer(nn.Module):
         both = torch.cat([self.lo, -self.hi])
         dist.all_reduce(both, op=dist.ReduceOp.MIN, group=group)
         self.lo.copy_(both[: self.n_mels])
-        self.hi.copy_(-both[self.n_mels:])
+        torch.neg(both[self.n_mels:], out=self.hi)
 
     def scale(self) -> Tensor:
         """K / (hi - lo) per channel, 0 where the channel is degenerate."""
@@ -153,7 +153,19 @@ class DMelQuantizer(nn.Module):
         if not check_after:
             self._check_ready()
         self._check_channels(z)
+        pending = None
+        if check_after and "ready" not in self._derived and self.lo.is_cuda:
+            # the flag travels to pinned host memory BEFORE the launch is queued and is awaited after it: the host
+            # learns it while the quantiser runs, and nothing sits behind the kernel on the stream
+            if getattr(self, "_flag_host", None) is None:
+                self._flag_host = torch.empty((), dtype=torch.bool).pin_memory()
+            self._flag_host.copy_(torch.all(self.lo <= self.hi), non_blocking=True)
+            pending = torch.cuda.Event()
+            pending.record(torch.cuda.current_stream(self.lo.device))
         codes = _plan.quantize(z, self.lo, self.scale(), self.n_bins, n_valid=mel_lengths)
+        if pending is not None:
+            pending.synchronize()
+            self._derived["ready"] = bool(self._flag_host.item())
         if check_after:
             self._check_ready()
         return codes

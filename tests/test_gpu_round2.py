@@ -31,6 +31,19 @@ def quant_golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "quantizer_golden.npz"))
 
 
+def test_deferred_calibration_check_still_raises(d):
+    """encode(check_after=True) queues the launch before it learns whether the statistics are usable (the job's pass 2
+    after the all-reduce); an uncalibrated quantiser must raise all the same, and work once calibrated"""
+    q = d.DMelQuantizer(8, 16).cuda()
+    mel = torch.randn(2, 8, 50, device="cuda")
+    with pytest.raises(RuntimeError):
+        q.encode(mel, check_after=True)
+    with pytest.raises(RuntimeError):
+        q.encode(mel)
+    q.update_stats(mel)
+    assert torch.equal(q.encode(mel, check_after=True), q.encode(mel))
+
+
 @pytest.mark.parametrize("shape", [(5, 7, 33), (3, 80, 626), (4, 16, 1), (2, 3, 10), (6, 128, 937)])
 @pytest.mark.parametrize("aligned", [True, False])
 def test_length_aware_quantiser_equals_quantise_then_mask(d, shape, aligned):
