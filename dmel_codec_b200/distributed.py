@@ -75,11 +75,10 @@ def calibrate_encode_sharded(tokenizer, n_utterances: int, load_batch: Callable[
     ``KEEP_MEL_HBM_FRACTION`` of the free HBM the job runs as the two transform passes instead."""
     rank, size = world()
     mine = shard_range(n_utterances, rank, size)
-    if not _shard_logmel_fits(tokenizer, mine, load_batch, batch_size):
-        # the shard's log-mel does not fit next to the waveforms: two transform passes instead, same codes
+    def two_passes():  # the shard's log-mel does not fit next to the waveforms: the transform runs twice, same codes
         calibrate_sharded(tokenizer, n_utterances, load_batch, batch_size, group=group)
         yield from encode_sharded(tokenizer, n_utterances, load_batch, batch_size)
-        return
+
     q = tokenizer.quantizer
     q.reset_stats()
     # Pass 1.  Batches of the shard's common padded length write straight into ONE store, so that pass 2 is a single
@@ -91,7 +90,16 @@ def calibrate_encode_sharded(tokenizer, n_utterances: int, load_batch: Callable[
         audios, lengths = item if isinstance(item, (tuple, list)) else (item, None)
         b, t = (audios.shape[0] if audios.ndim > 1 else 1), tokenizer.n_frames(audios.shape[-1])
         if store is None:
-            store = torch.empty((len(mine), q.n_mels, t), dtype=torch.float32, device=audios.device)
+            # the first batch gives the shard's frame count: decide here whether the store fits (every rank ends up with
+            # exactly one all-reduce whichever way it decides, so ranks need not agree)
+            try:
+                if not _store_fits(4 * len(mine) * q.n_mels * t, audios.device):
+                    raise torch.cuda.OutOfMemoryError("the shard's log-mel does not fit")
+                store = _alloc_store((len(mine), q.n_mels, t), audios.device)
+            except torch.cuda.OutOfMemoryError:
+                del item, audios, lengths
+                yield from two_passes()
+                return
         if store is not None and t == store.shape[2] and used + b <= store.shape[0] and audios.device == store.device:
             tokenizer.update_stats_keep_mel(audios, lengths, out=store[used:used + b])
             kept.append((ids, lengths, used, None))
@@ -135,23 +143,26 @@ def _mask_past(codes: torch.Tensor, code_lengths: torch.Tensor) -> torch.Tensor:
 KEEP_MEL_HBM_FRACTION = 0.6
 
 
-def _shard_logmel_fits(tokenizer, ids: Sequence[int], load_batch, batch_size: int) -> bool:
-    """Whether 4 bytes per log-mel value of this rank's shard fit in free HBM.  The size is estimated from the
-    first batch (utterances of a shard are of similar length by construction of a bucketing sampler, reference
-    dataset/lhotse_tts_dataset.py:184-191); DMEL_KEEP_MEL=0/1 overrides the decision."""
+def _alloc_store(shape, device) -> torch.Tensor:
+    return torch.empty(shape, dtype=torch.float32, device=device)
+
+
+def _store_fits(need: int, device) -> bool:
+    """Whether ``need`` bytes of log-mel fit in this GPU's free HBM next to everything else (DMEL_KEEP_MEL=0/1 overrides
+    the decision).  The driver's free-memory query is a synchronising call that now and then takes milliseconds, and
+    this process's own allocator counters are host-side: when the store needs less than a quarter of what this process
+    has not reserved yet it fits unless another process holds three quarters of the GPU (then the allocation fails
+    and the caller falls back), so only the tight cases ask the driver."""
     import os
     forced = os.environ.get("DMEL_KEEP_MEL")
     if forced is not None:
         return forced != "0"
-    if len(ids) == 0:
+    device = torch.device(device)
+    if device.type != "cuda":
         return True
-    item = load_batch(ids[:batch_size])
-    audios = item[0] if isinstance(item, (tuple, list)) else item
-    if not audios.is_cuda:
+    total = torch.cuda.get_device_properties(device).total_memory
+    unreserved = total - torch.cuda.memory_reserved(device)
+    if KEEP_MEL_HBM_FRACTION > 0 and need <= 0.25 * KEEP_MEL_HBM_FRACTION * unreserved:
         return True
-    frames = audios.shape[-1] // tokenizer.hop_length
-    need = 4 * len(ids) * tokenizer.quantizer.n_mels * frames
-    if need <= (1 << 30) * KEEP_MEL_HBM_FRACTION and KEEP_MEL_HBM_FRACTION > 0:
-        return True  # under a GiB: not worth a driver query on a 180 GB part
-    free, _total = torch.cuda.mem_get_info(audios.device)
+    free, _total = torch.cuda.mem_get_info(device)
     return need <= KEEP_MEL_HBM_FRACTION * free

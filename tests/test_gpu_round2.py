@@ -290,6 +290,16 @@ def test_hbm_fit_fallback_of_the_single_transform_job(d, monkeypatch):
     assert torch.equal(a.quantizer.lo, b.quantizer.lo) and torch.equal(a.quantizer.hi, b.quantizer.hi)
     for (_, cw, _), (_, cg, _) in zip(want, got):
         assert torch.equal(cw, cg)
+    # ... and when the estimate said yes but the allocation fails (another process took the memory in between)
+    monkeypatch.setattr(D, "KEEP_MEL_HBM_FRACTION", 0.6)
+
+    def no_memory(shape, device):
+        raise torch.cuda.OutOfMemoryError("simulated")
+
+    monkeypatch.setattr(D, "_alloc_store", no_memory)
+    c = _tokenizer(d, kw, 16)
+    again = list(D.calibrate_encode_sharded(c, 6, load, 4))
+    assert torch.equal(a.quantizer.lo, c.quantizer.lo) and all(torch.equal(cw, cg) for (_, cw, _), (_, cg, _) in zip(want, again))
 
 
 # ---------------------------------------------------------------------------
