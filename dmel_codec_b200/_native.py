@@ -82,6 +82,7 @@ SIGNATURES = {
                                  c_void_p, c_void_p]),
     "dmel_quantize_masked_u8": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_int,
                                         c_void_p, c_void_p]),
+    "dmel_quantizer_derive_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dmel_dequantize_f32": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_int, c_void_p,
                                     c_void_p]),
     "dmel_tensor_minmax_f32": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p,

@@ -1150,6 +1150,19 @@ int dmel_tensor_minmax_f32(const float* logmel_dev, long long n_rows, int n_mels
   return DMEL_OK;
 }
 
+int dmel_quantizer_derive_f32(const float* lo_dev, const float* hi_dev, int n_mels, int n_bins, float* scale_dev,
+                              float* step_dev, int32_t* ready_dev, void* stream) {
+  if (!lo_dev || !hi_dev) return fail(DMEL_ERR_INVALID, "lo_dev / hi_dev is null");
+  if (n_mels < 1) return fail(DMEL_ERR_INVALID, "n_mels must be positive, got %d", n_mels);
+  int rc = check_bins(n_bins);
+  if (rc != DMEL_OK) return rc;
+  if (!scale_dev && !step_dev && !ready_dev) return fail(DMEL_ERR_INVALID, "no output requested");
+  DeviceGuard guard(device_of(lo_dev));
+  DMEL_CUDA(launch_pdl(dmel::quantizer_derive_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, lo_dev, hi_dev, n_mels,
+                       (float)n_bins, scale_dev, step_dev, reinterpret_cast<int*>(ready_dev)));
+  return DMEL_OK;
+}
+
 static int fsq_levels(const int* levels, int n_levels, dmel::FsqLevels* lv) {
   if (!levels || n_levels < 1 || n_levels > dmel::kFsqMaxDims)
     return fail(DMEL_ERR_INVALID, "n_levels must be in [1, %d], got %d", dmel::kFsqMaxDims, n_levels);

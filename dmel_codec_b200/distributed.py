@@ -147,12 +147,14 @@ def _alloc_store(shape, device) -> torch.Tensor:
     return torch.empty(shape, dtype=torch.float32, device=device)
 
 
+_TOTAL_HBM = {}  # device index -> bytes (asked once: even the allocator's statistics cost 50 us per query)
+
+
 def _store_fits(need: int, device) -> bool:
-    """Whether ``need`` bytes of log-mel fit in this GPU's free HBM next to everything else (DMEL_KEEP_MEL=0/1 overrides
-    the decision).  The driver's free-memory query is a synchronising call that now and then takes milliseconds, and
-    this process's own allocator counters are host-side: when the store needs less than a quarter of what this process
-    has not reserved yet it fits unless another process holds three quarters of the GPU (then the allocation fails
-    and the caller falls back), so only the tight cases ask the driver."""
+    """Whether ``need`` bytes of log-mel fit in this GPU's HBM next to everything else (DMEL_KEEP_MEL=0/1 overrides the
+    decision).  The driver's free-memory query is a synchronising call that now and then takes milliseconds, so only
+    the tight cases ask it: a store under a quarter of ``KEEP_MEL_HBM_FRACTION`` of the GPU's memory is taken to fit,
+    and if the allocation then fails (this or another process holds the memory) the caller falls back."""
     import os
     forced = os.environ.get("DMEL_KEEP_MEL")
     if forced is not None:
@@ -160,9 +162,10 @@ def _store_fits(need: int, device) -> bool:
     device = torch.device(device)
     if device.type != "cuda":
         return True
-    total = torch.cuda.get_device_properties(device).total_memory
-    unreserved = total - torch.cuda.memory_reserved(device)
-    if KEEP_MEL_HBM_FRACTION > 0 and need <= 0.25 * KEEP_MEL_HBM_FRACTION * unreserved:
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    if index not in _TOTAL_HBM:
+        _TOTAL_HBM[index] = torch.cuda.get_device_properties(index).total_memory
+    if KEEP_MEL_HBM_FRACTION > 0 and need <= 0.25 * KEEP_MEL_HBM_FRACTION * _TOTAL_HBM[index]:
         return True
     free, _total = torch.cuda.mem_get_info(device)
     return need <= KEEP_MEL_HBM_FRACTION * free

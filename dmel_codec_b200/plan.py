@@ -410,6 +410,20 @@ def quantize(mel: torch.Tensor, lo: torch.Tensor, scale: torch.Tensor, n_bins: i
     return codes
 
 
+def quantizer_derive(lo: torch.Tensor, hi: torch.Tensor, n_bins: int):
+    """(scale, step, ready) of a CUDA quantiser's statistics in one launch: K / (hi - lo) or 0, (hi - lo) / K, and an
+    int32 device flag that is 1 iff lo <= hi on every channel."""
+    _require_cuda(lo, "lo")
+    m = lo.numel()
+    _require_stat(lo, "lo", lo.device, m)
+    _require_stat(hi, "hi", lo.device, m)
+    scale, step = torch.empty_like(lo), torch.empty_like(lo)
+    ready = torch.empty((), dtype=torch.int32, device=lo.device)
+    _native.check(_native.load().dmel_quantizer_derive_f32(
+        lo.data_ptr(), hi.data_ptr(), m, int(n_bins), scale.data_ptr(), step.data_ptr(), ready.data_ptr(), _stream_ptr(lo.device)))
+    return scale, step, ready
+
+
 def dequantize(codes: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
     _require_cuda(codes, "codes")
     if codes.ndim != 3 or codes.dtype != torch.uint8:

@@ -72,10 +72,26 @@ class DMelQuantizer(nn.Module):
         return super()._load_from_state_dict(*args, **kwargs)
 
     # -- statistics -----------------------------------------------------------
+    def _derive(self) -> None:
+        """scale, step and the device-side "is calibrated" flag: one launch on CUDA, the same arithmetic in torch ops
+        on the CPU (where only the oracle-backed tests run)."""
+        if "scale" in self._derived:
+            return
+        if self.lo.is_cuda:
+            scale, step, flag = _plan.quantizer_derive(self.lo, self.hi, self.n_bins)
+        else:
+            width = self.hi - self.lo
+            # a true float32 division K / width (scalar / tensor would be reciprocal-then-multiply: other bits)
+            scale = torch.where(width > 0, torch.full_like(width, float(self.n_bins)) / width, torch.zeros_like(width))
+            step = (width / float(self.n_bins)).contiguous()
+            flag = torch.all(self.lo <= self.hi).to(torch.int32)
+        self._derived.update(scale=scale, step=step, ready_flag=flag)
+
     @property
     def calibrated(self) -> bool:
         if "ready" not in self._derived:
-            self._derived["ready"] = bool(torch.all(self.lo <= self.hi).item())
+            self._derive()
+            self._derived["ready"] = bool(self._derived["ready_flag"].item())
         return self._derived["ready"]
 
     def reset_stats(self) -> None:
@@ -112,18 +128,12 @@ class DMelQuantizer(nn.Module):
 
     def scale(self) -> Tensor:
         """K / (hi - lo) per channel, 0 where the channel is degenerate."""
-        if "scale" not in self._derived:
-            width = self.hi - self.lo
-            # a true float32 division K / width (scalar / tensor would be reciprocal-then-multiply: other bits); K is
-            # filled on the device, so nothing is copied from the host
-            k = torch.full_like(width, float(self.n_bins))
-            self._derived["scale"] = torch.where(width > 0, k / width, torch.zeros_like(width))
+        self._derive()
         return self._derived["scale"]
 
     def step(self) -> Tensor:
         """(hi - lo) / K per channel: the bin width the centre table is built from."""
-        if "step" not in self._derived:
-            self._derived["step"] = ((self.hi - self.lo) / float(self.n_bins)).contiguous()
+        self._derive()
         return self._derived["step"]
 
     def host_stats(self):
@@ -158,8 +168,9 @@ class DMelQuantizer(nn.Module):
             # the flag travels to pinned host memory BEFORE the launch is queued and is awaited after it: the host
             # learns it while the quantiser runs, and nothing sits behind the kernel on the stream
             if getattr(self, "_flag_host", None) is None:
-                self._flag_host = torch.empty((), dtype=torch.bool).pin_memory()
-            self._flag_host.copy_(torch.all(self.lo <= self.hi), non_blocking=True)
+                self._flag_host = torch.empty((), dtype=torch.int32).pin_memory()
+            self._derive()
+            self._flag_host.copy_(self._derived["ready_flag"], non_blocking=True)
             pending = torch.cuda.Event()
             pending.record(torch.cuda.current_stream(self.lo.device))
         codes = _plan.quantize(z, self.lo, self.scale(), self.n_bins, n_valid=mel_lengths)

@@ -274,6 +274,12 @@ int dmel_quantize_masked_u8(const float* logmel_dev, long long n_rows, int n_mel
 int dmel_dequantize_f32(const uint8_t* codes_dev, long long n_rows, int n_mels, long long n_frames,
                         const float* table_dev, int n_bins, float* logmel_dev, void* stream);
 
+/* What the quantiser derives from its statistics, one launch; each output may be NULL:
+ *   scale_dev[c] = hi - lo > 0 ? n_bins / (hi - lo) : 0     step_dev[c] = (hi - lo) / n_bins     (float32, IEEE division)
+ *   *ready_dev   = 1 iff lo[c] <= hi[c] for every channel: the statistics have seen at least one frame. */
+int dmel_quantizer_derive_f32(const float* lo_dev, const float* hi_dev, int n_mels, int n_bins, float* scale_dev,
+                              float* step_dev, int32_t* ready_dev, void* stream);
+
 /* Running min/max over valid frames of an existing log-mel tensor
  * (n_valid_dev: frames per row, or NULL). Updates min_dev / max_dev in place. */
 int dmel_tensor_minmax_f32(const float* logmel_dev, long long n_rows, int n_mels, long long n_frames,

@@ -31,6 +31,31 @@ def quant_golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "quantizer_golden.npz"))
 
 
+def test_derived_quantities_in_one_launch_equal_the_spec(d):
+    """dmel_quantizer_derive_f32: scale = K / (hi - lo) or 0, step = (hi - lo) / K (float32 divisions, bit for bit what
+    the torch formulas of SURVEY.md Appendix B give) and the calibrated flag, incl. a degenerate channel, an unseen
+    channel (+inf / -inf) and an inverted one"""
+    from dmel_codec_b200 import plan as P
+    g = torch.Generator().manual_seed(5)
+    lo = torch.randn(131, generator=g) * 3 - 8
+    hi = lo + torch.rand(131, generator=g) * 12 + 1e-3
+    hi[7] = lo[7]                                   # degenerate: scale 0
+    for k in (1, 16, 32, 255, 256):
+        scale, step, ready = P.quantizer_derive(lo.cuda(), hi.cuda(), k)
+        width = hi - lo
+        assert torch.equal(scale.cpu(), torch.where(width > 0, torch.full_like(width, float(k)) / width, torch.zeros_like(width)))
+        assert torch.equal(step.cpu(), width / float(k)) and int(ready) == 1
+    lo2, hi2 = lo.clone(), hi.clone()
+    lo2[3], hi2[3] = float("inf"), float("-inf")    # a channel that never saw a frame
+    scale, step, ready = P.quantizer_derive(lo2.cuda(), hi2.cuda(), 16)
+    assert int(ready) == 0 and scale[3].item() == 0.0
+    q = d.DMelQuantizer(131, 16).cuda()
+    q.set_stats(lo, hi)
+    assert q.calibrated and torch.equal(q.scale().cpu(), torch.where(width > 0, torch.full_like(width, 16.0) / width, torch.zeros_like(width)))
+    q.set_stats(lo2, hi2)
+    assert not q.calibrated
+
+
 def test_deferred_calibration_check_still_raises(d):
     """encode(check_after=True) queues the launch before it learns whether the statistics are usable (the job's pass 2
     after the all-reduce); an uncalibrated quantiser must raise all the same, and work once calibrated"""
